@@ -1,0 +1,278 @@
+"""
+CPU oracle for the ALS / item-kNN hot paths — TEST INFRASTRUCTURE ONLY.
+
+Thin ctypes binding of ``oracle/liblk_oracle.so`` (``oracle/lk_oracle.c``, a C
+restatement of ``src/accel/als/*.rs`` and ``src/accel/knn/*.rs``).  Only
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this package; nothing under
+``lkpy_b200/`` does.  See the header of ``lk_oracle.c`` for how it is pinned.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import scipy.sparse as sps
+
+_DIR = Path(__file__).resolve().parent
+_LIB_PATH = _DIR / "liblk_oracle.so"
+_lib = None
+
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> Path:
+    """Compile the oracle with the committed Makefile (gcc, no GPU needed)."""
+    src = _DIR / "lk_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_DIR), "-s"], check=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(_LIB_PATH))
+        L.lk_oracle_set_blas.argtypes = [C.c_void_p, C.c_void_p]
+        L.lk_oracle_set_blas.restype = None
+        L.lk_oracle_max_threads.restype = C.c_int
+        L.lk_oracle_bf16_round.argtypes = [_f32p, _f32p, C.c_int64]
+        L.lk_oracle_bf16_round.restype = None
+        L.lk_oracle_posv_f32.argtypes = [_f32p, _f32p, C.c_int]
+        L.lk_oracle_posv_f32.restype = C.c_int
+        L.lk_oracle_otor.argtypes = [_f32p, C.c_int64, C.c_int, C.c_float, C.c_int, _f32p, _f64p]
+        L.lk_oracle_otor.restype = None
+        L.lk_oracle_als_half_f32.argtypes = [
+            C.c_int, _i64p, _i32p, _f32p, C.c_int64, C.c_int, _f32p, _f32p, C.c_void_p,
+            C.c_float, C.c_int, C.c_int, C.POINTER(C.c_double),
+        ]  # fmt: skip
+        L.lk_oracle_als_half_f32.restype = C.c_int64
+        L.lk_oracle_als_half_f64.argtypes = [
+            C.c_int, _i64p, _i32p, _f32p, C.c_int64, C.c_int, _f32p, _f64p, _f32p, C.c_void_p,
+            C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double),
+        ]  # fmt: skip
+        L.lk_oracle_als_half_f64.restype = C.c_int64
+        L.lk_oracle_knn_build.argtypes = [
+            _i64p, _i32p, _f32p, _i64p, _i32p, _f32p, C.c_int64, C.c_int64, C.c_float,
+            C.c_int64, C.c_int64, C.c_int64, C.c_int,
+        ]  # fmt: skip
+        L.lk_oracle_knn_build.restype = C.c_void_p
+        for nm, rt in (
+            ("lk_oracle_csr_indptr", C.POINTER(C.c_int64)),
+            ("lk_oracle_csr_cols", C.POINTER(C.c_int32)),
+            ("lk_oracle_csr_vals", C.POINTER(C.c_float)),
+            ("lk_oracle_csr_rows", C.c_int64),
+        ):
+            getattr(L, nm).argtypes = [C.c_void_p]
+            getattr(L, nm).restype = rt
+        L.lk_oracle_csr_free.argtypes = [C.c_void_p]
+        L.lk_oracle_csr_free.restype = None
+        L.lk_oracle_knn_score.argtypes = [
+            _i64p, _i32p, _f32p, C.c_int64, _i32p, C.c_void_p, C.c_int64, _i32p, C.c_int64,
+            C.c_int, C.c_int, _f32p, _i32p,
+        ]  # fmt: skip
+        L.lk_oracle_knn_score.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _capsule_ptr(module, name: str) -> int:
+    cap = module.__pyx_capi__[name]
+    C.pythonapi.PyCapsule_GetName.restype = C.c_char_p
+    C.pythonapi.PyCapsule_GetName.argtypes = [C.py_object]
+    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    return C.pythonapi.PyCapsule_GetPointer(cap, C.pythonapi.PyCapsule_GetName(cap))
+
+
+def use_scipy_blas(enable: bool = True) -> None:
+    """
+    Route the per-row solve through SciPy's bundled LAPACK ``sposv`` — the
+    routine the reference resolves at ``src/accel/als/solve.rs:47-58`` via the
+    same ``__pyx_capi__`` capsule — and the Gram through OpenBLAS ``sgemm``
+    (the role of ``matrixmultiply`` at ``implicit.rs:112``).
+    """
+    if enable:
+        from scipy.linalg import cython_blas, cython_lapack
+
+        lib().lk_oracle_set_blas(
+            _capsule_ptr(cython_lapack, "sposv"), _capsule_ptr(cython_blas, "sgemm")
+        )
+    else:
+        lib().lk_oracle_set_blas(None, None)
+
+
+def max_threads() -> int:
+    return int(lib().lk_oracle_max_threads())
+
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    lib().lk_oracle_bf16_round(x.reshape(-1), out.reshape(-1), x.size)
+    return out
+
+
+def posv(A: np.ndarray, b: np.ndarray) -> tuple[np.ndarray, int]:
+    A = np.array(A, dtype=np.float32, order="C")
+    x = np.array(b, dtype=np.float32, order="C")
+    info = lib().lk_oracle_posv_f32(A, x, len(x))
+    return x, int(info)
+
+
+def otor(other: np.ndarray, reg: float, bf16: bool = False) -> tuple[np.ndarray, np.ndarray]:
+    """``_implicit_otor`` (als/_implicit.py:177-184): (f32-accumulated, f64-accumulated)."""
+    other = np.ascontiguousarray(other, dtype=np.float32)
+    n, k = other.shape
+    o32 = np.empty((k, k), dtype=np.float32)
+    o64 = np.empty((k, k), dtype=np.float64)
+    lib().lk_oracle_otor(other, n, k, reg, int(bf16), o32, o64)
+    return o32, o64
+
+
+def _csr_parts(m):
+    """Accept an ``InteractionCSR``-like object or a SciPy CSR."""
+    if hasattr(m, "indptr") and hasattr(m, "indices"):
+        indptr, cols = m.indptr, m.indices
+        vals = m.values if hasattr(m, "values") else m.data
+    else:
+        raise TypeError("expected CSR")
+    return (
+        np.ascontiguousarray(indptr, dtype=np.int64),
+        np.ascontiguousarray(cols, dtype=np.int32),
+        np.ascontiguousarray(vals, dtype=np.float32),
+    )
+
+
+def als_half(
+    mode: str,
+    matrix,
+    this: np.ndarray,
+    other: np.ndarray,
+    *,
+    otor_mat: np.ndarray | None = None,
+    reg: float = 0.0,
+    bf16_other: bool = False,
+    threads: int = 0,
+) -> tuple[np.ndarray, float]:
+    """
+    One f32 ALS half-epoch (``train_implicit_matrix`` / ``train_explicit_matrix``).
+    Returns (new ``this``, sqrt(sum ||delta||^2)); the input is not modified.
+    """
+    indptr, cols, vals = _csr_parts(matrix)
+    this = np.array(this, dtype=np.float32, order="C")
+    other = np.ascontiguousarray(other, dtype=np.float32)
+    n_rows, k = this.shape
+    m = 0 if mode == "implicit" else 1
+    op = None
+    if m == 0:
+        assert otor_mat is not None
+        otor_mat = np.ascontiguousarray(otor_mat, dtype=np.float32)
+        op = otor_mat.ctypes.data_as(C.c_void_p)
+    sq = C.c_double(0.0)
+    fail = lib().lk_oracle_als_half_f32(
+        m, indptr, cols, vals, n_rows, k, this, other, op, reg, int(bf16_other), threads, C.byref(sq)
+    )
+    if fail:
+        raise RuntimeError(f"ALS solve error: row {fail - 1} not positive definite")
+    return this, float(np.sqrt(sq.value))
+
+
+def als_half_f64(
+    mode: str,
+    matrix,
+    this: np.ndarray,
+    other: np.ndarray,
+    *,
+    otor_mat: np.ndarray | None = None,
+    reg: float = 0.0,
+    bf16_other: bool = False,
+    threads: int = 0,
+) -> tuple[np.ndarray, float]:
+    """f64 tolerance oracle of the same half-epoch; returns a float64 matrix."""
+    indptr, cols, vals = _csr_parts(matrix)
+    this = np.ascontiguousarray(this, dtype=np.float32)
+    other = np.ascontiguousarray(other, dtype=np.float32)
+    n_rows, k = this.shape
+    out = np.empty((n_rows, k), dtype=np.float64)
+    m = 0 if mode == "implicit" else 1
+    op = None
+    if m == 0:
+        assert otor_mat is not None
+        otor_mat = np.ascontiguousarray(otor_mat, dtype=np.float64)
+        op = otor_mat.ctypes.data_as(C.c_void_p)
+    sq = C.c_double(0.0)
+    fail = lib().lk_oracle_als_half_f64(
+        m, indptr, cols, vals, n_rows, k, this, out, other, op, reg, int(bf16_other), threads,
+        C.byref(sq),
+    )  # fmt: skip
+    if fail:
+        raise RuntimeError(f"ALS solve error: row {fail - 1} not positive definite")
+    return out, float(np.sqrt(sq.value))
+
+
+def knn_build(
+    ui, iu, min_sim: float, save_nbrs: int | None, rows: tuple[int, int] | None = None, threads: int = 0
+) -> sps.csr_array:
+    """``compute_similarities`` (item_train.rs:32-152) → CSR with int64 offsets."""
+    uip, uic, uiv = _csr_parts(ui)
+    iup, iuc, iuv = _csr_parts(iu)
+    n_users = len(uip) - 1
+    n_items = len(iup) - 1
+    rb, re = rows if rows is not None else (0, n_items)
+    L = lib()
+    h = L.lk_oracle_knn_build(
+        uip, uic, uiv, iup, iuc, iuv, n_users, n_items, np.float32(min_sim),
+        int(save_nbrs) if save_nbrs else 0, rb, re, threads,
+    )  # fmt: skip
+    try:
+        nr = L.lk_oracle_csr_rows(h)
+        indptr = np.ctypeslib.as_array(L.lk_oracle_csr_indptr(h), shape=(nr + 1,)).copy()
+        nnz = int(indptr[-1])
+        if nnz:
+            cols = np.ctypeslib.as_array(L.lk_oracle_csr_cols(h), shape=(nnz,)).copy()
+            vals = np.ctypeslib.as_array(L.lk_oracle_csr_vals(h), shape=(nnz,)).copy()
+        else:
+            cols = np.empty(0, dtype=np.int32)
+            vals = np.empty(0, dtype=np.float32)
+    finally:
+        L.lk_oracle_csr_free(h)
+    return sps.csr_array((vals, cols, indptr), shape=(nr, n_items))
+
+
+def knn_score(
+    sims: sps.csr_array,
+    ref_items: np.ndarray,
+    ref_vals: np.ndarray | None,
+    tgt_items: np.ndarray,
+    max_nbrs: int,
+    min_nbrs: int,
+) -> tuple[np.ndarray, np.ndarray]:
+    """``score_explicit`` / ``score_implicit`` (item_score.rs:22-111); NaN / -1 mark nulls."""
+    indptr = np.ascontiguousarray(sims.indptr, dtype=np.int64)
+    cols = np.ascontiguousarray(sims.indices, dtype=np.int32)
+    vals = np.ascontiguousarray(sims.data, dtype=np.float32)
+    ref_items = np.ascontiguousarray(ref_items, dtype=np.int32)
+    tgt_items = np.ascontiguousarray(tgt_items, dtype=np.int32)
+    rv = None
+    if ref_vals is not None:
+        ref_vals = np.ascontiguousarray(ref_vals, dtype=np.float32)
+        rv = ref_vals.ctypes.data_as(C.c_void_p)
+    scores = np.empty(len(tgt_items), dtype=np.float32)
+    counts = np.empty(len(tgt_items), dtype=np.int32)
+    rc = lib().lk_oracle_knn_score(
+        indptr, cols, vals, sims.shape[0], ref_items, rv, len(ref_items), tgt_items,
+        len(tgt_items), max_nbrs, min_nbrs, scores, counts,
+    )  # fmt: skip
+    if rc == 1:
+        raise ValueError("similarity is null")
+    if rc:
+        raise IndexError("item index out of range")
+    return scores, counts
