@@ -1,0 +1,70 @@
+"""
+In-tree build of the CUDA library ``lkpy_b200/csrc/liblkpy_b200.so`` for sm_100a.
+
+``nvcc`` cross-compiles without a GPU, so this runs in the CPU build container;
+the resulting ``.so`` is git-ignored but travels to the GPU box with the tree.
+"""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB = CSRC / "liblkpy_b200.so"
+SOURCES = ["capi.cu", "als_kernels.cu", "knn_build.cu", "knn_score.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+]  # fmt: skip
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh"]
+    deps.append(CSRC.parent.parent / "include" / "lkpy_b200.h")
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not _stale():
+        return LIB
+    nvcc = _nvcc()
+    objdir = CSRC / "build"
+    objdir.mkdir(exist_ok=True)
+    env = dict(os.environ)
+    # the image's CC/CXX point at a wrapper without OpenMP specs; nvcc wants the system g++
+    env.pop("CC", None)
+    env.pop("CXX", None)
+
+    def one(src: str) -> Path:
+        obj = objdir / (src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True, env=env)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(one, SOURCES))
+    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-ccbin", "/usr/bin/g++", "-o", str(LIB), *map(str, objs)]
+    subprocess.run(cmd, check=True, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

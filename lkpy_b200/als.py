@@ -1,0 +1,386 @@
+"""
+ALS scorers on the B200 engine — the component surface of ``lenskit.als``.
+
+Mirrors (same names, config fields and aliases, training/epoch contract):
+
+* ``ALSConfig`` / ``ImplicitMFConfig`` / ``BiasedMFConfig``
+  (``src/lenskit/als/_common.py:36-78``, ``_implicit.py:24-32``, ``_explicit.py:25-29``)
+* ``ImplicitMFScorer`` / ``BiasedMFScorer`` and their trainers
+  (``_implicit.py:35-175``, ``_explicit.py:32-118``, ``_common.py:113-356``)
+
+What differs: factor tables and the two CSR orientations live in HBM for the
+whole training run; a half-epoch is ``lk_als_otor`` + ``lk_als_half_epoch`` on
+the device; ``user_embeddings`` / ``item_embeddings`` are materialised on the
+host after every epoch (the model must be usable after each ``train_epoch()``,
+``training.py:364-370``).  The engine-only option ``gather_dtype="bfloat16"``
+gathers a bf16 copy of the opposite factor table (BASELINE.json config 2).
+"""
+
+from __future__ import annotations
+
+from typing import Literal
+
+import numpy as np
+import torch
+from pydantic import AliasChoices, BaseModel, Field, PositiveFloat, PositiveInt
+
+from . import _lib, engine
+from .components import Component, Dataset, ItemList, ModelTrainer, RecQuery, TrainingOptions, UsesTrainer
+from .data import InteractionCSR, Interactions
+
+
+class ALSConfig(BaseModel):
+    embedding_size: PositiveInt = Field(default=64, validation_alias=AliasChoices("embedding_size", "features"))
+    epochs: PositiveInt = 10
+    regularization: PositiveFloat | tuple[PositiveFloat, PositiveFloat] = 0.1
+    user_embeddings: bool | Literal["prefer"] = True
+    gather_dtype: Literal["float32", "bfloat16"] = "float32"
+    "Engine option: storage type of the gathered (opposite) factor rows."
+
+    @property
+    def user_reg(self) -> float:
+        r = self.regularization
+        return float(r[0]) if isinstance(r, tuple) else float(r)
+
+    @property
+    def item_reg(self) -> float:
+        r = self.regularization
+        return float(r[1]) if isinstance(r, tuple) else float(r)
+
+
+class ImplicitMFConfig(ALSConfig):
+    weight: float = 40
+    use_ratings: bool = False
+
+
+class BiasedMFConfig(ALSConfig):
+    damping: float | tuple[float, float] = 5.0
+
+
+def _as_dataset(data) -> Dataset:
+    if isinstance(data, Dataset):
+        return data
+    if isinstance(data, Interactions):
+        return Dataset(data)
+    raise TypeError("expected a Dataset or Interactions")
+
+
+class ALSBase(UsesTrainer, Component):
+    """``ALSBase`` (als/_common.py:113-192)."""
+
+    users = None
+    items = None
+    user_embeddings: np.ndarray | None = None
+    item_embeddings: np.ndarray | None = None
+
+    def is_trained(self) -> bool:
+        return self.item_embeddings is not None
+
+    def new_user_embedding(self, user_num, items: ItemList):  # pragma: no cover
+        raise NotImplementedError
+
+    def finalize_scores(self, user_num, items: ItemList, user_bias) -> ItemList:
+        return items
+
+    def __call__(self, query, items: ItemList) -> ItemList:
+        query = RecQuery.create(query)
+        user_num = None
+        if query.user_id is not None and self.users is not None:
+            user_num = self.users.number(query.user_id, missing=None)
+        u_offset = None
+        u_feat = None
+        if (
+            query.query_items is not None
+            and len(query.query_items) > 0
+            and self.config.user_embeddings != "prefer"
+        ):
+            u_feat, u_offset = self.new_user_embedding(user_num, query.query_items)
+        if u_feat is None:
+            if user_num is None or self.user_embeddings is None:
+                return ItemList(items, scores=np.nan)
+            u_feat = self.user_embeddings[user_num, :]
+        item_nums = items.numbers(vocabulary=self.items, missing="negative")
+        mask = item_nums >= 0
+        scores = np.full((len(items),), np.nan, dtype=np.float32)
+        scores[mask] = self.item_embeddings[item_nums[mask], :] @ u_feat
+        return self.finalize_scores(user_num, ItemList(items, scores=scores), u_offset)
+
+
+def _solve_cholesky(A: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """``lenskit.math.solve.solve_cholesky`` (math/solve.py:17-41); host fold-in only."""
+    from scipy.linalg import cho_factor, cho_solve
+
+    return np.require(cho_solve(cho_factor(A), y), dtype=A.dtype)
+
+
+class ALSTrainerBase(ModelTrainer):
+    """``ALSTrainerBase`` (als/_common.py:195-356) with device-resident state."""
+
+    MODE = _lib.LK_ALS_IMPLICIT
+    kernel_events: list | None = None  # bench.py: (start, end) CUDA events around each row-solve launch
+
+    def __init__(self, scorer: ALSBase, data, options: TrainingOptions):
+        self.scorer = scorer
+        ds = _as_dataset(data)
+        self.device = _lib.require_device()
+        scorer.users = ds.users
+        scorer.items = ds.items
+        self.rng = options.random_generator()
+        k = self.config.embedding_size
+
+        coo = self.prepare_matrix(ds)
+        self.ui_host = InteractionCSR.from_scipy(coo)
+        self.iu_host = InteractionCSR.from_scipy(coo.T)
+        self.ui = engine.DeviceCSR.from_host(self.ui_host, self.device)
+        self.iu = engine.DeviceCSR.from_host(self.iu_host, self.device)
+        self.u_plan = engine.ALSHalfPlan.create(self.ui, k)
+        self.i_plan = engine.ALSHalfPlan.create(self.iu, k)
+        self.otor_ws = engine.OtorWorkspace.create(k, self.device)
+
+        # items first, then users, from one generator (als/_common.py:287-301)
+        q0 = self.initial_params(ds.item_count, k)
+        p0 = self.initial_params(ds.user_count, k)
+        self.d_items = torch.from_numpy(q0).to(self.device)
+        self.d_users = torch.from_numpy(p0).to(self.device)
+        self.bf16 = self.config.gather_dtype == "bfloat16"
+        self.d_items_bf16 = torch.empty_like(self.d_items, dtype=torch.bfloat16) if self.bf16 else None
+        self.d_users_bf16 = torch.empty_like(self.d_users, dtype=torch.bfloat16) if self.bf16 else None
+        self.epochs_trained = 0
+        self._sync_host()
+
+    @property
+    def config(self):
+        return self.scorer.config
+
+    # -- hooks -------------------------------------------------------------
+    def prepare_matrix(self, data: Dataset):  # pragma: no cover
+        raise NotImplementedError
+
+    def initial_params(self, nrows: int, ncols: int) -> np.ndarray:  # pragma: no cover
+        raise NotImplementedError
+
+    # -- epoch ---------------------------------------------------------------
+    def _half(self, plan, this, other, other_bf16, reg: float) -> torch.Tensor:
+        plan.sqdelta.zero_()
+        otor = None
+        gather = other
+        if self.MODE == _lib.LK_ALS_IMPLICIT:
+            otor = engine.als_otor(other, reg, self.otor_ws, other_bf16)
+            if other_bf16 is not None:
+                gather = other_bf16
+        elif other_bf16 is not None:
+            other_bf16.copy_(other)
+            gather = other_bf16
+        if self.kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        engine.als_half_epoch(plan, self.MODE, this, gather, otor=otor, reg=reg)
+        if self.kernel_events is not None:
+            e1.record()
+            self.kernel_events.append((e0, e1))
+        return plan.sqdelta
+
+    def train_epoch_device(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """One epoch entirely on the device; returns the two Σ‖Δ‖² scalars (device)."""
+        self.u_plan.status.zero_()
+        self.i_plan.status.zero_()
+        du = self._half(self.u_plan, self.d_users, self.d_items, self.d_items_bf16, self.config.user_reg)
+        di = self._half(self.i_plan, self.d_items, self.d_users, self.d_users_bf16, self.config.item_reg)
+        self.epochs_trained += 1
+        return du, di
+
+    def _raise_on_status(self) -> None:
+        for plan in (self.u_plan, self.i_plan):
+            st = int(plan.status.item())
+            if st:
+                raise RuntimeError(f"ALS solve error: array minor of row {st - 1} is not positive")
+
+    def train_epoch(self) -> dict[str, float]:
+        du, di = self.train_epoch_device()
+        self._sync_host()
+        self._raise_on_status()
+        return {"deltaP": float(np.sqrt(du.item())), "deltaQ": float(np.sqrt(di.item()))}
+
+    def train_epoch_e2e(self, host_users: torch.Tensor, host_items: torch.Tensor) -> dict[str, float]:
+        """
+        One epoch with the factor tables taken from, and returned to, pinned host
+        tensors (the host-array contract of ``train_*_matrix``); the CSR stays in HBM.
+        """
+        self.d_users.copy_(host_users, non_blocking=True)
+        self.d_items.copy_(host_items, non_blocking=True)
+        du, di = self.train_epoch_device()
+        host_users.copy_(self.d_users, non_blocking=True)
+        host_items.copy_(self.d_items, non_blocking=True)
+        deltas = torch.cat([du, di]).cpu()  # device->host read of the step's result; synchronises
+        return {"deltaP": float(np.sqrt(deltas[0])), "deltaQ": float(np.sqrt(deltas[1]))}
+
+    def _sync_host(self) -> None:
+        self.scorer.user_embeddings = self.d_users.cpu().numpy()
+        self.scorer.item_embeddings = self.d_items.cpu().numpy()
+
+    def finalize(self) -> None:
+        self._sync_host()
+        if not self.config.user_embeddings:
+            self.scorer.user_embeddings = None
+            self.scorer.users = None
+
+    def get_parameters(self) -> dict[str, object]:
+        return {"user_embeddings": self.scorer.user_embeddings, "item_embeddings": self.scorer.item_embeddings}
+
+    def load_parameters(self, state) -> None:
+        self.d_users.copy_(torch.from_numpy(np.ascontiguousarray(state["user_embeddings"], dtype=np.float32)))
+        self.d_items.copy_(torch.from_numpy(np.ascontiguousarray(state["item_embeddings"], dtype=np.float32)))
+        self._sync_host()
+
+
+# ---------------------------------------------------------------------------
+# implicit feedback
+# ---------------------------------------------------------------------------
+
+
+class ImplicitMFScorer(ALSBase):
+    """``ImplicitMFScorer`` (als/_implicit.py:35-130)."""
+
+    CONFIG_CLASS = ImplicitMFConfig
+    config: ImplicitMFConfig
+    _OtOr: np.ndarray
+
+    def create_trainer(self, data, options):
+        return ImplicitMFTrainer(self, data, options)
+
+    def new_user_embedding(self, user_num, user_items: ItemList):
+        ri = user_items.numbers(vocabulary=self.items, missing="negative")
+        good = ri >= 0
+        if self.config.use_ratings:
+            ratings = user_items.field("rating")
+            if ratings is None:
+                raise ValueError("no ratings in user items")
+            val = ratings[good] * self.config.weight
+        else:
+            val = np.full((int(good.sum()),), self.config.weight)
+        val = val.astype(self.item_embeddings.dtype)
+        M = self.item_embeddings[ri[good], :]
+        A = self._OtOr + (M.T * val) @ M
+        y = M.T @ (val + 1.0)
+        return _solve_cholesky(A, y.astype(A.dtype)), None
+
+
+class ImplicitMFTrainer(ALSTrainerBase):
+    MODE = _lib.LK_ALS_IMPLICIT
+
+    def prepare_matrix(self, data: Dataset):
+        it = data.interactions
+        base = it.ratings if self.config.use_ratings else np.ones(it.nnz, dtype=np.float32)
+        vals = (np.require(base, dtype=np.float32) * self.config.weight).astype(np.float32)
+        return it.coo(vals)
+
+    def initial_params(self, nrows: int, ncols: int) -> np.ndarray:
+        mat = self.rng.standard_normal((nrows, ncols), dtype=np.float32) * 0.01
+        mat *= mat
+        return mat
+
+    def _save_user_otor(self) -> None:
+        q = self.scorer.item_embeddings
+        self.scorer._OtOr = q.T @ q + np.eye(q.shape[1], dtype=q.dtype) * self.config.user_reg
+
+    def train_epoch(self):
+        res = super().train_epoch()
+        self._save_user_otor()
+        return res
+
+    def finalize(self):
+        self._sync_host()
+        self._save_user_otor()
+        super().finalize()
+
+
+# ---------------------------------------------------------------------------
+# explicit feedback
+# ---------------------------------------------------------------------------
+
+
+class BiasModel:
+    """The part of ``lenskit.basic.BiasModel`` (basic/bias.py:84-150) BiasedMF needs."""
+
+    def __init__(self, global_bias, item_biases, user_biases, damping):
+        self.global_bias = global_bias
+        self.item_biases = item_biases
+        self.user_biases = user_biases
+        self.damping = damping
+
+    @classmethod
+    def learn(cls, it: Interactions, damping) -> "BiasModel":
+        d_user, d_item = damping if isinstance(damping, tuple) else (damping, damping)
+        g = float(np.mean(it.ratings))
+        centered = it.ratings.astype(np.float64) - g
+        counts = np.full(it.n_items, float(d_item))
+        sums = np.zeros(it.n_items)
+        np.add.at(counts, it.items, 1)
+        np.add.at(sums, it.items, centered)
+        ib = np.zeros(it.n_items, dtype=np.float32)
+        np.divide(sums, counts, out=ib, where=counts > 0, casting="unsafe")
+        centered = centered - ib[it.items]
+        counts = np.full(it.n_users, float(d_user))
+        sums = np.zeros(it.n_users)
+        np.add.at(counts, it.users, 1)
+        np.add.at(sums, it.users, centered)
+        ub = np.zeros(it.n_users, dtype=np.float32)
+        np.divide(sums, counts, out=ub, where=counts > 0, casting="unsafe")
+        return cls(g, ib, ub, (d_user, d_item))
+
+    def transform(self, it: Interactions) -> np.ndarray:
+        return (it.ratings - self.global_bias - self.item_biases[it.items] - self.user_biases[it.users]).astype(
+            np.float32
+        )
+
+
+class BiasedMFScorer(ALSBase):
+    """``BiasedMFScorer`` (als/_explicit.py:32-91)."""
+
+    CONFIG_CLASS = BiasedMFConfig
+    config: BiasedMFConfig
+    bias: BiasModel
+
+    def create_trainer(self, data, options):
+        return BiasedMFTrainer(self, data, options)
+
+    def new_user_embedding(self, user_num, items: ItemList):
+        inums = items.numbers(vocabulary=self.items, missing="negative")
+        ratings = items.field("rating")
+        assert ratings is not None
+        mask = (inums >= 0) & np.isfinite(ratings)
+        uoff = ratings - self.bias.global_bias
+        uoff[inums >= 0] -= self.bias.item_biases[inums[inums >= 0]]
+        u_bias = float(np.sum(uoff) / (np.sum(np.isfinite(uoff)) + self.bias.damping[0]))
+        biases = np.full(len(items), self.bias.global_bias, dtype=np.float32)
+        biases[inums >= 0] += self.bias.item_biases[inums[inums >= 0]]
+        rv = (ratings - biases - u_bias)[mask].astype(np.float32)
+        nf = self.item_embeddings.shape[1]
+        if mask.sum() == 0:
+            return np.zeros(nf, dtype=np.float32), u_bias
+        M = self.item_embeddings[inums[mask], :]
+        A = M.T @ M + np.eye(nf, dtype=np.float32) * self.config.user_reg * int(mask.sum())
+        return np.require(_solve_cholesky(A, (M.T @ rv).astype(A.dtype)), dtype=np.float32), u_bias
+
+    def finalize_scores(self, user_num, items: ItemList, user_bias) -> ItemList:
+        scores = items.scores()
+        if user_bias is None:
+            user_bias = float(self.bias.user_biases[user_num]) if user_num is not None else 0.0
+        inums = items.numbers(vocabulary=self.items, missing="negative")
+        biases = np.full(len(items), self.bias.global_bias + user_bias, dtype=np.float32)
+        biases[inums >= 0] += self.bias.item_biases[inums[inums >= 0]]
+        return ItemList(items, scores=scores + biases)
+
+
+class BiasedMFTrainer(ALSTrainerBase):
+    MODE = _lib.LK_ALS_EXPLICIT
+
+    def prepare_matrix(self, data: Dataset):
+        it = data.interactions
+        self.scorer.bias = BiasModel.learn(it, self.config.damping)
+        return it.coo(self.scorer.bias.transform(it))
+
+    def initial_params(self, nrows: int, ncols: int) -> np.ndarray:
+        mat = self.rng.standard_normal((nrows, ncols), dtype=np.float32)
+        mat /= np.linalg.norm(mat, axis=1).reshape((nrows, 1))
+        return mat

@@ -1,0 +1,232 @@
+// knn_score.cu — batched item-kNN neighbourhood scoring for sm_100a.
+//
+// Replaces src/accel/knn/item_score.rs:22-111 (score_explicit / score_implicit)
+// and the ScoreAccumulator of src/accel/knn/accum.rs:16-239, batched over many
+// queries (the reference scores one query per call, single-threaded).
+//
+// Semantics kept exactly:
+//   * reference items are visited in history order, each one's similarity row
+//     in column order; a target's accumulator takes the first `max_nbrs`
+//     contributions as a vector (accum.rs:86-98) whose sums are taken in push
+//     order — reproduced here by running sums updated in the same order;
+//   * a target that receives more than `max_nbrs` contributions switches to a
+//     min-heap (accum.rs:73-82,100-117).  Those targets are re-scored by a
+//     per-lane emulation of the Rust std BinaryHeap element movement so that
+//     the survivor set under ties and the summation order match;
+//   * null (negative) reference items are skipped, null targets give NaN / -1.
+//
+// One warp owns one query: lanes spread over the entries of a similarity row,
+// history entries are processed one after the other (order is the contract).
+// A per-warp `slotmap` (n_items ints, kept at -1 between queries) maps item ->
+// position in the query's target list, so cost is proportional to the
+// contributions and the target list, never to n_items.
+
+#include "common.cuh"
+
+namespace lk {
+
+struct AccEnt {
+    float w, v;
+};
+
+// heap order is reversed on weight (accum.rs:166-178): a <= b  <=>  b.w <= a.w
+__device__ __forceinline__ bool ent_le(const AccEnt &a, const AccEnt &b) { return b.w <= a.w; }
+
+__device__ void heap_sift_up(AccEnt *d, int start, int pos)
+{
+    AccEnt hole = d[pos];
+    while (pos > start) {
+        const int parent = (pos - 1) / 2;
+        if (ent_le(hole, d[parent])) break;
+        d[pos] = d[parent];
+        pos = parent;
+    }
+    d[pos] = hole;
+}
+
+__device__ void heap_pop(AccEnt *d, int &len)
+{
+    AccEnt item = d[--len];
+    if (len > 0) {
+        AccEnt top = d[0];
+        d[0] = item;
+        item = top;
+        // sift_down_to_bottom(0) then sift_up
+        const int end = len;
+        int pos = 0;
+        AccEnt hole = d[0];
+        int child = 1;
+        while (end >= 2 && child <= end - 2) {
+            if (ent_le(d[child], d[child + 1])) child += 1;
+            d[pos] = d[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) {
+            d[pos] = d[child];
+            pos = child;
+        }
+        d[pos] = hole;
+        heap_sift_up(d, 0, pos);
+    }
+}
+
+constexpr int SCORE_MAX_NBRS = 128;  // heap re-scoring keeps max_nbrs+1 entries in local memory
+
+// exact ScoreAccumulator replay for one (query, target) pair
+__device__ void rescore_exact(const lk_knn_score_args &a, int64_t r0, int64_t r1, int t, float *out_ws,
+                              float *out_tw, int *out_len)
+{
+    AccEnt d[SCORE_MAX_NBRS + 1];
+    int len = 0;
+    bool is_heap = false;
+    const int limit = a.max_nbrs;
+    for (int64_t p = r0; p < r1; p++) {
+        const int r = a.d_ref_items[p];
+        if (r < 0 || r >= a.n_items) continue;
+        int64_t lo = a.d_sim_indptr[r], hi = a.d_sim_indptr[r + 1];
+        const int64_t end = hi;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (a.d_sim_cols[mid] < t) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= end || a.d_sim_cols[lo] != t) continue;
+        AccEnt e;
+        e.w = a.d_sim_vals[lo];
+        e.v = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
+        if (!is_heap && len < limit) {
+            d[len++] = e;
+        } else {
+            if (!is_heap) {  // Partial -> Full: pop from the back, push (accum.rs:73-82)
+                AccEnt tmp[SCORE_MAX_NBRS + 1];
+                const int n = len;
+                for (int i = 0; i < n; i++) tmp[i] = d[i];
+                len = 0;
+                for (int i = n - 1; i >= 0; i--) {
+                    d[len++] = tmp[i];
+                    heap_sift_up(d, 0, len - 1);
+                }
+                is_heap = true;
+            }
+            if (e.w > d[0].w) {  // accum.rs:107
+                d[len++] = e;
+                heap_sift_up(d, 0, len - 1);
+                while (len > limit) heap_pop(d, len);
+            }
+        }
+    }
+    float tw = 0.0f, ws = 0.0f;
+    for (int i = 0; i < len; i++) tw = __fadd_rn(tw, d[i].w);
+    for (int i = 0; i < len; i++) ws = __fadd_rn(ws, __fmul_rn(d[i].w, d[i].v));
+    *out_ws = ws;
+    *out_tw = tw;
+    *out_len = len;
+}
+
+__global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int32_t *slotmap = a.d_slotmap + (size_t)gwarp * a.n_items;
+    const bool explicit_fb = a.d_ref_vals != nullptr;
+    const float qnan = __int_as_float(0x7fc00000);
+
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(a.d_work_counter, 1);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= a.n_queries) break;
+        const int64_t t0 = a.d_tgt_indptr[q], t1 = a.d_tgt_indptr[q + 1];
+        const int64_t r0 = a.d_ref_indptr[q], r1 = a.d_ref_indptr[q + 1];
+
+        // 1. register the targets, zero their accumulator state
+        for (int64_t x = t0 + lane; x < t1; x += 32) {
+            const int t = a.d_tgt_items[x];
+            a.d_acc_ws[x] = 0.0f;
+            a.d_acc_tw[x] = 0.0f;
+            a.d_acc_cnt[x] = 0;
+            if (t >= 0 && t < a.n_items) slotmap[t] = (int32_t)(x - t0);
+        }
+        __syncwarp();
+
+        // 2. contributions in history order; one similarity row's entries hit distinct targets
+        for (int64_t p = r0; p < r1; p++) {
+            const int r = a.d_ref_items[p];
+            if (r < 0 || r >= a.n_items) continue;  // null reference item
+            const float rv = explicit_fb ? a.d_ref_vals[p] : 0.0f;
+            const int64_t s0 = a.d_sim_indptr[r], s1 = a.d_sim_indptr[r + 1];
+            for (int64_t e = s0 + lane; e < s1; e += 32) {
+                const int t = a.d_sim_cols[e];
+                const int32_t slot = slotmap[t];
+                if (slot >= 0) {
+                    const float sim = a.d_sim_vals[e];
+                    if (sim != sim) atomicCAS(a.d_status, 0, 2);  // "similarity is null" (accum.rs:146-152)
+                    const int64_t x = t0 + slot;
+                    const int c = a.d_acc_cnt[x];
+                    if (c < a.max_nbrs) {  // vector state: sums in push order
+                        a.d_acc_tw[x] = __fadd_rn(a.d_acc_tw[x], sim);
+                        if (explicit_fb) a.d_acc_ws[x] = __fadd_rn(a.d_acc_ws[x], __fmul_rn(sim, rv));
+                    }
+                    a.d_acc_cnt[x] = c + 1;
+                }
+            }
+            __syncwarp();
+        }
+
+        // 3. finalise every target position (duplicate targets read the registered slot)
+        for (int64_t x = t0 + lane; x < t1; x += 32) {
+            const int t = a.d_tgt_items[x];
+            float score = qnan;
+            int count = -1;
+            if (t >= 0 && t < a.n_items) {
+                const int64_t xs = t0 + slotmap[t];
+                int c = a.d_acc_cnt[xs];
+                float ws = a.d_acc_ws[xs], tw = a.d_acc_tw[xs];
+                if (c > a.max_nbrs) rescore_exact(a, r0, r1, t, &ws, &tw, &c);  // heap state
+                count = c;
+                if (c >= a.min_nbrs) score = explicit_fb ? ws / tw : tw;
+            }
+            a.d_scores[x] = score;
+            a.d_counts[x] = count;
+        }
+        __syncwarp();
+        for (int64_t x = t0 + lane; x < t1; x += 32) {
+            const int t = a.d_tgt_items[x];
+            if (t >= 0 && t < a.n_items) slotmap[t] = -1;
+        }
+        __syncwarp();
+    }
+}
+
+constexpr int SCORE_WARPS_PER_SM = 16;
+
+}  // namespace lk
+
+using namespace lk;
+
+extern "C" {
+
+int64_t lk_knn_score_warps(void) { return (int64_t)sm_count() * SCORE_WARPS_PER_SM; }
+
+int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
+{
+    LK_REQUIRE(args != nullptr, LK_ERR_INVALID, "lk_knn_score_batch: null args");
+    const lk_knn_score_args &a = *args;
+    LK_REQUIRE(a.n_items >= 1 && a.n_queries >= 0, LK_ERR_INVALID, "bad shape");
+    LK_REQUIRE(a.max_nbrs >= 1 && a.max_nbrs <= SCORE_MAX_NBRS, LK_ERR_UNSUPPORTED,
+               "max_nbrs must be in 1..%d", SCORE_MAX_NBRS);
+    LK_REQUIRE(a.d_sim_indptr && a.d_sim_cols && a.d_sim_vals && a.d_ref_indptr && a.d_ref_items &&
+                   a.d_tgt_indptr && a.d_tgt_items && a.d_slotmap && a.d_acc_ws && a.d_acc_tw &&
+                   a.d_acc_cnt && a.d_scores && a.d_counts && a.d_work_counter && a.d_status,
+               LK_ERR_INVALID, "lk_knn_score_batch: null pointer");
+    LK_REQUIRE(a.slotmap_warps >= lk_knn_score_warps(), LK_ERR_INVALID, "slotmap too small");
+    if (a.n_queries == 0) return LK_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LK_CUDA_TRY(cudaMemsetAsync(a.d_work_counter, 0, sizeof(int32_t), st));
+    const int blocks = sm_count() * SCORE_WARPS_PER_SM / 8;
+    knn_score_kernel<<<blocks, 256, 0, st>>>(a);
+    LK_CUDA_TRY(cudaGetLastError());
+    return LK_OK;
+}
+
+}  // extern "C"

@@ -142,8 +142,10 @@ def synth_interactions(
         us = np.searchsorted(ucdf, rng.random(want), side="right").astype(np.int64)
         ranks = np.searchsorted(icdf, rng.random(want), side="right")
         its = perm[ranks].astype(np.int64)
-        new = np.unique(us * n_items + its)
-        keys = np.union1d(keys, new) if len(keys) else new
+        new = np.sort(us * n_items + its)  # np.unique is far slower than sort + mask here
+        if len(keys):
+            new = np.sort(np.concatenate([keys, new]))
+        keys = new[np.concatenate([[True], new[1:] != new[:-1]])] if len(new) else new
         if len(keys) >= nnz:
             break
     if len(keys) < nnz:

@@ -1,0 +1,407 @@
+"""
+Device-side engine: torch tensors in, C-ABI calls out.
+
+PyTorch is used for device memory, streams and (in ``lkpy_b200.parallel``)
+``torch.distributed`` only.  Every compute step is a call into
+``liblkpy_b200.so``; nothing here falls back to torch math.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LkAlsArgs, LkKnnBuildArgs, LkKnnGeom, LkKnnScoreArgs, check, lib, ptr, stream_ptr
+from .data import InteractionCSR
+
+DEFAULT_CHUNK_NNZ = 4096
+
+
+@dataclass
+class DeviceCSR:
+    """A CSR matrix resident in HBM (int32 offsets/indices, f32 values)."""
+
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    values: torch.Tensor
+    shape: tuple[int, int]
+    h_indptr: np.ndarray  # host copy of the offsets, for planning
+
+    @classmethod
+    def from_host(cls, m: InteractionCSR, device=None, pin: bool = False) -> "DeviceCSR":
+        device = device or _lib.require_device()
+        if m.indptr.dtype != np.int32:
+            raise _lib.EngineError("matrices with nnz >= 2**31 need row sharding first")
+
+        def up(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if pin:
+                t = t.pin_memory()
+            return t.to(device, non_blocking=pin)
+
+        return cls(up(m.indptr), up(m.indices), up(m.values), m.shape, np.ascontiguousarray(m.indptr))
+
+    @property
+    def nnz(self) -> int:
+        return int(self.h_indptr[-1])
+
+
+# ---------------------------------------------------------------------------
+# ALS
+# ---------------------------------------------------------------------------
+
+
+@dataclass
+class ALSHalfPlan:
+    """Row-chunk schedule and workspaces for one side (user or item) of ALS."""
+
+    matrix: DeviceCSR
+    k: int
+    chunk_nnz: int
+    chunks: torch.Tensor
+    n_chunks: int
+    n_split_rows: int
+    n_slots: int
+    partials: torch.Tensor | None
+    split_counters: torch.Tensor | None
+    work_counter: torch.Tensor
+    sqdelta: torch.Tensor
+    status: torch.Tensor
+
+    @classmethod
+    def create(cls, matrix: DeviceCSR, k: int, chunk_nnz: int = DEFAULT_CHUNK_NNZ) -> "ALSHalfPlan":
+        L = lib()
+        dev = matrix.indptr.device
+        n_rows = matrix.shape[0]
+        hp = matrix.h_indptr
+        nc, ns, nslot = C.c_int64(), C.c_int64(), C.c_int64()
+        check(
+            L.lk_als_plan_size(hp.ctypes.data, n_rows, chunk_nnz, C.byref(nc), C.byref(ns), C.byref(nslot)),
+            "lk_als_plan_size",
+        )
+        h_chunks = np.empty((max(nc.value, 1), 8), dtype=np.int32)
+        check(L.lk_als_plan_fill(hp.ctypes.data, n_rows, chunk_nnz, h_chunks.ctypes.data), "lk_als_plan_fill")
+        slot_f = L.lk_als_slot_floats(k)
+        if slot_f < 0:
+            raise _lib.EngineError(f"embedding size {k} not supported (max {L.lk_als_max_features()})")
+        partials = counters = None
+        if ns.value > 0:
+            partials = torch.empty(nslot.value * slot_f, dtype=torch.float32, device=dev)
+            counters = torch.zeros(ns.value, dtype=torch.int32, device=dev)
+        return cls(
+            matrix=matrix,
+            k=k,
+            chunk_nnz=chunk_nnz,
+            chunks=torch.from_numpy(h_chunks).to(dev),
+            n_chunks=nc.value,
+            n_split_rows=ns.value,
+            n_slots=nslot.value,
+            partials=partials,
+            split_counters=counters,
+            work_counter=torch.zeros(1, dtype=torch.int32, device=dev),
+            sqdelta=torch.zeros(1, dtype=torch.float64, device=dev),
+            status=torch.zeros(1, dtype=torch.int32, device=dev),
+        )
+
+
+@dataclass
+class OtorWorkspace:
+    scratch: torch.Tensor
+    otor: torch.Tensor
+
+    @classmethod
+    def create(cls, k: int, device) -> "OtorWorkspace":
+        n = lib().lk_als_otor_scratch_floats(k)
+        if n < 0:
+            raise _lib.EngineError(f"embedding size {k} not supported")
+        return cls(
+            torch.empty(n, dtype=torch.float32, device=device),
+            torch.empty((k, k), dtype=torch.float32, device=device),
+        )
+
+
+def als_otor(
+    other: torch.Tensor, reg: float, ws: OtorWorkspace, other_bf16: torch.Tensor | None = None
+) -> torch.Tensor:
+    """OtOr = OᵀO + reg·I on device; optionally fills the bf16 copy of ``other``."""
+    assert other.dtype == torch.float32 and other.is_contiguous()
+    n, k = other.shape
+    if other_bf16 is not None:
+        assert other_bf16.dtype == torch.bfloat16 and other_bf16.shape == other.shape
+    check(
+        lib().lk_als_otor(ptr(other), n, k, float(reg), ptr(ws.otor), ptr(other_bf16), ptr(ws.scratch), stream_ptr()),
+        "lk_als_otor",
+    )
+    return ws.otor
+
+
+def als_half_epoch(
+    plan: ALSHalfPlan,
+    mode: int,
+    this: torch.Tensor,
+    other: torch.Tensor,
+    *,
+    otor: torch.Tensor | None = None,
+    reg: float = 0.0,
+    replicas: list[torch.Tensor] | None = None,
+    replica_row0: int = 0,
+) -> None:
+    """
+    Enqueue one half-epoch.  ``this`` [n_rows,k] f32 is updated in place;
+    ``other`` is f32 or bf16.  ``plan.sqdelta`` accumulates Σ‖Δ‖² and
+    ``plan.status`` reports a non-PD row; the caller zeroes / reads them.
+    """
+    m = plan.matrix
+    assert this.dtype == torch.float32 and this.is_contiguous()
+    assert other.is_contiguous() and other.shape[1] == this.shape[1] == plan.k
+    assert this.shape[0] == m.shape[0] and other.shape[0] == m.shape[1]
+    a = LkAlsArgs()
+    a.mode = mode
+    a.k = plan.k
+    a.n_rows = m.shape[0]
+    a.n_other = other.shape[0]
+    a.d_indptr, a.d_cols, a.d_vals = ptr(m.indptr), ptr(m.indices), ptr(m.values)
+    a.d_this = ptr(this)
+    a.d_other = ptr(other)
+    if other.dtype == torch.float32:
+        a.other_dtype = _lib.LK_DTYPE_F32
+    elif other.dtype == torch.bfloat16:
+        a.other_dtype = _lib.LK_DTYPE_BF16
+    else:
+        raise TypeError(f"unsupported factor dtype {other.dtype}")
+    reps = replicas or []
+    a.n_replicas = len(reps)
+    for i, r in enumerate(reps):
+        a.d_replicas[i] = r if isinstance(r, int) else ptr(r)
+    a.replica_row0 = replica_row0
+    a.d_otor = ptr(otor)
+    a.reg = float(reg)
+    a.d_chunks = ptr(plan.chunks)
+    a.n_chunks = plan.n_chunks
+    a.d_partials = ptr(plan.partials)
+    a.d_split_counters = ptr(plan.split_counters)
+    a.n_split_rows = plan.n_split_rows
+    a.d_work_counter = ptr(plan.work_counter)
+    a.d_sqdelta = ptr(plan.sqdelta)
+    a.d_status = ptr(plan.status)
+    check(lib().lk_als_half_epoch(C.byref(a), stream_ptr()), "lk_als_half_epoch")
+
+
+# ---------------------------------------------------------------------------
+# item-kNN build
+# ---------------------------------------------------------------------------
+
+
+@dataclass
+class KnnBuildPlan:
+    """Tiling, tile pointers and cost-ordered work list for one (UI, IU) pair."""
+
+    ui: DeviceCSR
+    iu: DeviceCSR
+    geom: LkKnnGeom
+    tile_ptr: torch.Tensor
+    cost: torch.Tensor  # int64 [n_items]
+    order: torch.Tensor  # int32 [n_items], most expensive first
+    tie_scratch: torch.Tensor
+    work_counter: torch.Tensor
+    status: torch.Tensor
+    extra: dict = field(default_factory=dict)
+
+    @classmethod
+    def create(cls, ui: DeviceCSR, iu: DeviceCSR) -> "KnnBuildPlan":
+        L = lib()
+        dev = ui.indptr.device
+        n_users, n_items = ui.shape
+        assert iu.shape == (n_items, n_users)
+        g = LkKnnGeom()
+        check(L.lk_knn_geometry(n_users, n_items, C.byref(g)), "lk_knn_geometry")
+        tile_ptr = torch.empty(max(1, n_users * (g.n_subtiles + 1)), dtype=torch.int32, device=dev)
+        check(
+            L.lk_knn_tile_pointers(C.byref(g), ptr(ui.indptr), ptr(ui.indices), ptr(tile_ptr), stream_ptr()),
+            "lk_knn_tile_pointers",
+        )
+        cost = torch.empty(n_items, dtype=torch.int64, device=dev)
+        check(
+            L.lk_knn_row_cost(C.byref(g), ptr(ui.indptr), ptr(iu.indptr), ptr(iu.indices), ptr(cost), stream_ptr()),
+            "lk_knn_row_cost",
+        )
+        order = torch.argsort(cost, descending=True, stable=True).to(torch.int32)
+        tie = torch.empty(max(1, L.lk_knn_tie_scratch_ints(C.byref(g))), dtype=torch.int32, device=dev)
+        return cls(
+            ui, iu, g, tile_ptr, cost, order, tie,
+            torch.zeros(1, dtype=torch.int32, device=dev),
+            torch.zeros(1, dtype=torch.int32, device=dev),
+        )  # fmt: skip
+
+    def _args(self, order: torch.Tensor, min_sim: float, save_nbrs: int) -> LkKnnBuildArgs:
+        a = LkKnnBuildArgs()
+        a.geom = self.geom
+        a.d_ui_indptr, a.d_ui_cols, a.d_ui_vals = ptr(self.ui.indptr), ptr(self.ui.indices), ptr(self.ui.values)
+        a.d_iu_indptr, a.d_iu_cols, a.d_iu_vals = ptr(self.iu.indptr), ptr(self.iu.indices), ptr(self.iu.values)
+        a.d_tile_ptr = ptr(self.tile_ptr)
+        a.d_order = ptr(order)
+        a.n_work = order.numel()
+        a.min_sim = float(np.float32(min_sim))
+        a.save_nbrs = int(save_nbrs)
+        a.d_tie_scratch = ptr(self.tie_scratch)
+        a.d_work_counter = ptr(self.work_counter)
+        a.d_status = ptr(self.status)
+        return a
+
+    def build_topk(
+        self, min_sim: float, save_nbrs: int, order: torch.Tensor | None = None
+    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """
+        Truncated build: returns fixed-width rows (cols [n_items,K] sorted by
+        column, vals, counts).  Rows not in ``order`` have count 0.
+        """
+        L = lib()
+        dev = self.ui.indptr.device
+        n_items, H, K = self.geom.n_items, self.geom.n_halves, int(save_nbrs)
+        order = self.order if order is None else order.to(torch.int32).contiguous()
+        part_cols = torch.empty(n_items * H * K, dtype=torch.int32, device=dev)
+        part_vals = torch.empty(n_items * H * K, dtype=torch.float32, device=dev)
+        part_cnt = torch.zeros(n_items * H, dtype=torch.int32, device=dev)
+        self.status.zero_()
+        a = self._args(order, min_sim, K)
+        a.d_part_cols, a.d_part_vals, a.d_part_cnt = ptr(part_cols), ptr(part_vals), ptr(part_cnt)
+        check(L.lk_knn_build(C.byref(a), stream_ptr()), "lk_knn_build")
+        out_cols = torch.empty((n_items, K), dtype=torch.int32, device=dev)
+        out_vals = torch.empty((n_items, K), dtype=torch.float32, device=dev)
+        out_cnt = torch.empty(n_items, dtype=torch.int32, device=dev)
+        check(
+            L.lk_knn_merge_topk(C.byref(a), ptr(out_cols), ptr(out_vals), ptr(out_cnt), stream_ptr()),
+            "lk_knn_merge_topk",
+        )
+        self.extra["keepalive"] = (part_cols, part_vals, part_cnt, order)
+        return out_cols, out_vals, out_cnt
+
+    def build_unbounded(
+        self, min_sim: float, order: torch.Tensor | None = None, capacity: int | None = None
+    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Unbounded build (``save_nbrs=None``): CSR (int64 indptr, cols, vals) on device."""
+        L = lib()
+        dev = self.ui.indptr.device
+        n_items, H = self.geom.n_items, self.geom.n_halves
+        order = self.order if order is None else order.to(torch.int32).contiguous()
+        if capacity is None:
+            # every kept pair shares a user: at most sum of the processed rows' product counts
+            capacity = int(min(int(self.cost[order.long()].sum().item()), order.numel() * max(n_items - 1, 1)))
+        capacity = max(capacity, 1)
+        pool_cols = torch.empty(capacity, dtype=torch.int32, device=dev)
+        pool_vals = torch.empty(capacity, dtype=torch.float32, device=dev)
+        pool_off = torch.zeros(n_items * H, dtype=torch.int64, device=dev)
+        part_cnt = torch.zeros(n_items * H, dtype=torch.int32, device=dev)
+        cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.status.zero_()
+        a = self._args(order, min_sim, 0)
+        a.d_part_cnt = ptr(part_cnt)
+        a.d_pool_cols, a.d_pool_vals, a.pool_capacity = ptr(pool_cols), ptr(pool_vals), capacity
+        a.d_pool_off, a.d_pool_cursor = ptr(pool_off), ptr(cursor)
+        check(L.lk_knn_build(C.byref(a), stream_ptr()), "lk_knn_build")
+        if int(self.status.item()) == 1:
+            raise _lib.EngineError("similarity pool overflow; pass a larger capacity")
+        counts = part_cnt.view(n_items, H).sum(dim=1, dtype=torch.int64)
+        indptr = torch.zeros(n_items + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        nnz = int(indptr[-1].item())
+        out_cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        out_vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        check(
+            L.lk_knn_pool_to_csr(C.byref(a), ptr(indptr), ptr(out_cols), ptr(out_vals), stream_ptr()),
+            "lk_knn_pool_to_csr",
+        )
+        torch.cuda.current_stream().synchronize()
+        return indptr, out_cols[:nnz], out_vals[:nnz]
+
+
+def topk_rows_to_csr(
+    cols: torch.Tensor, vals: torch.Tensor, cnt: torch.Tensor
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Compact fixed-width top-K rows into CSR (int64 offsets, the LargeList layout)."""
+    n, K = cols.shape
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=cols.device)
+    torch.cumsum(cnt.to(torch.int64), 0, out=indptr[1:])
+    mask = torch.arange(K, device=cols.device)[None, :] < cnt[:, None]
+    return indptr, cols[mask], vals[mask]
+
+
+# ---------------------------------------------------------------------------
+# item-kNN scoring
+# ---------------------------------------------------------------------------
+
+
+@dataclass
+class KnnScorerState:
+    """Similarity matrix in HBM plus the per-warp slot maps."""
+
+    n_items: int
+    sim_indptr: torch.Tensor  # int64
+    sim_cols: torch.Tensor
+    sim_vals: torch.Tensor
+    slotmap: torch.Tensor
+    slotmap_warps: int
+    work_counter: torch.Tensor
+    status: torch.Tensor
+
+    @classmethod
+    def create(cls, n_items: int, indptr, cols, vals, device=None) -> "KnnScorerState":
+        device = device or _lib.require_device()
+        warps = int(lib().lk_knn_score_warps())
+
+        def dev(t, dt):
+            t = torch.as_tensor(t)
+            return t.to(device=device, dtype=dt).contiguous()
+
+        return cls(
+            n_items,
+            dev(indptr, torch.int64),
+            dev(cols, torch.int32),
+            dev(vals, torch.float32),
+            torch.full((warps * n_items,), -1, dtype=torch.int32, device=device),
+            warps,
+            torch.zeros(1, dtype=torch.int32, device=device),
+            torch.zeros(1, dtype=torch.int32, device=device),
+        )
+
+    def score(
+        self,
+        ref_indptr: torch.Tensor,
+        ref_items: torch.Tensor,
+        ref_vals: torch.Tensor | None,
+        tgt_indptr: torch.Tensor,
+        tgt_items: torch.Tensor,
+        max_nbrs: int,
+        min_nbrs: int,
+    ) -> tuple[torch.Tensor, torch.Tensor]:
+        """Score a batch of queries; returns (scores with NaN nulls, counts with -1 nulls)."""
+        dev = self.sim_cols.device
+        nq = ref_indptr.numel() - 1
+        nt = tgt_items.numel()
+        scores = torch.empty(max(nt, 1), dtype=torch.float32, device=dev)
+        counts = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+        acc_ws = torch.empty(max(nt, 1), dtype=torch.float32, device=dev)
+        acc_tw = torch.empty(max(nt, 1), dtype=torch.float32, device=dev)
+        acc_cnt = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
+        self.status.zero_()
+        a = LkKnnScoreArgs()
+        a.n_items = self.n_items
+        a.d_sim_indptr, a.d_sim_cols, a.d_sim_vals = ptr(self.sim_indptr), ptr(self.sim_cols), ptr(self.sim_vals)
+        a.n_queries = nq
+        a.d_ref_indptr, a.d_ref_items, a.d_ref_vals = ptr(ref_indptr), ptr(ref_items), ptr(ref_vals)
+        a.d_tgt_indptr, a.d_tgt_items = ptr(tgt_indptr), ptr(tgt_items)
+        a.max_nbrs, a.min_nbrs = int(max_nbrs), int(min_nbrs)
+        a.d_slotmap, a.slotmap_warps = ptr(self.slotmap), self.slotmap_warps
+        a.d_acc_ws, a.d_acc_tw, a.d_acc_cnt = ptr(acc_ws), ptr(acc_tw), ptr(acc_cnt)
+        a.d_scores, a.d_counts = ptr(scores), ptr(counts)
+        a.d_work_counter, a.d_status = ptr(self.work_counter), ptr(self.status)
+        check(lib().lk_knn_score_batch(C.byref(a), stream_ptr()), "lk_knn_score_batch")
+        # keep scratch alive until the stream has consumed it
+        torch.cuda.current_stream().synchronize()
+        if int(self.status.item()) == 2:
+            raise ValueError("similarity is null")
+        return scores[:nt], counts[:nt]
