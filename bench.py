@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )  # fmt: skip
@@ -260,13 +260,15 @@ def run_reference(args, rank: int) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget per path")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--score-users", type=int, default=2048)
+    ap.add_argument("--variants", default="bf16,fp32", help="ALS gather dtypes to time (profiling runs pass one)")
+    ap.add_argument("--profile", action="store_true", help="under ncu: honour a small --warmup, skip e2e")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -308,7 +310,10 @@ def main() -> None:
 
     results: dict = {}
     launches = 0
+    variants = [v for v in args.variants.split(",") if v]
     for tag, gdt in (("bf16", "bfloat16"), ("fp32", "float32")):
+        if tag not in variants:
+            continue
         if world > 1:
             from lkpy_b200.parallel import ShardedImplicitMFTrainer
 
@@ -318,7 +323,7 @@ def main() -> None:
             scorer = ImplicitMFScorer(features=K, epochs=1, regularization=REG, weight=WEIGHT, gather_dtype=gdt)
             tr = ImplicitMFTrainer(scorer, ds, TrainingOptions(rng=42))
         # one epoch from the reference init first, so timed epochs see trained-scale factors
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
             tr.train_epoch_device()
         barrier()
         tr.kernel_events = []
@@ -365,7 +370,7 @@ def main() -> None:
             f"{achieved:.0f} GB/s algorithmic = {achieved / peak:.3f} of {peak_src}")
 
         # ---- end to end through the trainer API: factors from / to pinned host memory
-        if tag == "bf16":
+        if tag == "bf16" and not args.profile:
             hp = torch.from_numpy(scorer.user_embeddings).pin_memory()
             hq = torch.from_numpy(scorer.item_embeddings).pin_memory()
             for _ in range(2):
@@ -415,7 +420,7 @@ def main() -> None:
             knn.pop(k_, None)
 
     if rank == 0:
-        head = results["bf16"]
+        head = results.get("bf16") or results["fp32"]
         line = {
             "metric": METRIC, "value": head["ms_per_epoch"], "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_epoch"],
@@ -429,7 +434,8 @@ def main() -> None:
             },
             "roofline": head["roofline"], "clocks": head["clocks"], "e2e": results.get("e2e"),
             "gpu_launches": launches, "cpu_baseline": cpu,
-            "als_fp32": {"ms_per_epoch": results["fp32"]["ms_per_epoch"], "roofline": results["fp32"]["roofline"]},
+            "als_fp32": ({"ms_per_epoch": results["fp32"]["ms_per_epoch"], "roofline": results["fp32"]["roofline"]}
+                         if "fp32" in results else None),
             "knn": knn,
         }  # fmt: skip
         print(json.dumps(line), flush=True)

@@ -20,6 +20,7 @@ import scipy.sparse as sps
 _DIR = Path(__file__).resolve().parent
 _LIB_PATH = _DIR / "liblk_oracle.so"
 _lib = None
+_blas_limit = None
 
 _i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -101,6 +102,14 @@ def use_scipy_blas(enable: bool = True) -> None:
     """
     if enable:
         from scipy.linalg import cython_blas, cython_lapack
+
+        try:  # BLAS threads = 1 inside the row-parallel region
+            import threadpoolctl
+
+            global _blas_limit
+            _blas_limit = threadpoolctl.threadpool_limits(limits=1, user_api="blas")
+        except Exception:  # noqa: BLE001
+            pass
 
         lib().lk_oracle_set_blas(
             _capsule_ptr(cython_lapack, "sposv"), _capsule_ptr(cython_blas, "sgemm")
