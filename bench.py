@@ -472,6 +472,19 @@ def bench_knn(args, inter, dev, peak, peak_src) -> dict:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    if os.environ.get("LK_BENCH_TRACE"):
+        # per-phase wall times with a sync after each phase (diagnostic only)
+        def tick(label, fn):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            log(f"[trace] {label}: {(time.perf_counter() - t) * 1e3:.2f} ms")
+            return r
+
+        p2 = tick("plan (geometry, tile pointers, cost, argsort)", lambda: engine.KnnBuildPlan.create(d_ui, d_iu))
+        r2 = tick("build_topk (accumulate + merge)", lambda: p2.build_topk(KNN_MIN_SIM, KNN_SAVE))
+        tick("rows -> CSR", lambda: engine.topk_rows_to_csr(*r2))
     # the accumulate kernel alone (same stream, events around the launch)
     import ctypes as C
 

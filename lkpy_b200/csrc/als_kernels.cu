@@ -177,11 +177,13 @@ __global__ void __launch_bounds__(AlsCfg<KP>::NT, AlsCfg<KP>::OCC) als_half_kern
         fence_proxy_async();
         cta_sync<NW>();
 
-        float acc[TM][TN];
+        // accumulators as column pairs: the inner product issues packed FFMA2
+        // (fma.rn.f32x2) — plain FFMA runs at half the fp32 rate on sm_100
+        float2 acc2[TM][TN / 2];
 #pragma unroll
         for (int i = 0; i < TM; i++)
 #pragma unroll
-            for (int c = 0; c < TN; c++) acc[i][c] = 0.0f;
+            for (int c = 0; c < TN / 2; c++) acc2[i][c] = make_float2(0.0f, 0.0f);
         float yacc[C::YPT];
 #pragma unroll
         for (int q = 0; q < C::YPT; q++) yacc[q] = 0.0f;
@@ -256,9 +258,12 @@ __global__ void __launch_bounds__(AlsCfg<KP>::NT, AlsCfg<KP>::OCC) als_half_kern
                     w = v;
                 }
 #pragma unroll
-                for (int i = 0; i < TM; i++)
+                for (int i = 0; i < TM; i++) {
+                    const float2 a2 = make_float2(ra[i], ra[i]);
 #pragma unroll
-                    for (int c = 0; c < TN; c++) acc[i][c] = fmaf(ra[i], cb[c], acc[i][c]);
+                    for (int c = 0; c < TN / 2; c++)
+                        acc2[i][c] = __ffma2_rn(a2, make_float2(cb[2 * c], cb[2 * c + 1]), acc2[i][c]);
+                }
 #pragma unroll
                 for (int q = 0; q < C::YPT; q++)
                     yacc[q] = fmaf(elt_to_f32(m[tid + q * NT]), w, yacc[q]);
@@ -269,6 +274,15 @@ __global__ void __launch_bounds__(AlsCfg<KP>::NT, AlsCfg<KP>::OCC) als_half_kern
             cB = cC;
             vB = vC;
         }
+
+        float acc[TM][TN];
+#pragma unroll
+        for (int i = 0; i < TM; i++)
+#pragma unroll
+            for (int c = 0; c < TN / 2; c++) {
+                acc[i][2 * c] = acc2[i][c].x;
+                acc[i][2 * c + 1] = acc2[i][c].y;
+            }
 
         // ---- rows split over several chunks: park the partial, last part reduces
         if (nparts > 1) {
