@@ -116,6 +116,9 @@ typedef struct lk_als_args {
     int32_t *d_work_counter; /* [1] zeroed by the call */
     double *d_sqdelta;       /* [1] += sum_rows ||x_new - x_old||^2 (caller zeroes) */
     int32_t *d_status;       /* [1] 0, or 1 + first row whose system was not PD (caller zeroes) */
+    int32_t vals_uniform;    /* 1 when every d_vals entry equals uniform_val (implicit feedback without
+                                ratings): lets the Gram run on the tensor cores as v * M^T M */
+    float uniform_val;
 } lk_als_args;
 
 LK_API int lk_als_half_epoch(const lk_als_args *args, void *stream);

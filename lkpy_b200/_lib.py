@@ -55,6 +55,8 @@ class LkAlsArgs(C.Structure):
         ("d_work_counter", vp),
         ("d_sqdelta", vp),
         ("d_status", vp),
+        ("vals_uniform", C.c_int32),
+        ("uniform_val", C.c_float),
     ]
 
 

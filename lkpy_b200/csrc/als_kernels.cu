@@ -29,7 +29,7 @@
 #include <numeric>
 #include <vector>
 
-#include "common.cuh"
+#include "als_common.cuh"
 
 namespace lk {
 
@@ -60,15 +60,6 @@ __host__ __device__ constexpr int als_smem_bytes()
     int uni = stage > chol ? stage : chol;
     // union | y[KP] | dinv[KP] | mbarriers | misc
     return uni + KP * 4 + KP * 4 + C::NSTAGE * 8 + 64;
-}
-
-template <int NW>
-__device__ __forceinline__ void cta_sync()
-{
-    if constexpr (NW == 1)
-        __syncwarp();
-    else
-        __syncthreads();
 }
 
 __device__ __forceinline__ void load_row_frag(const float *m, float *dst, int n)
@@ -362,122 +353,9 @@ __global__ void __launch_bounds__(AlsCfg<KP>::NT, AlsCfg<KP>::OCC) als_half_kern
         for (int q = 0; q < C::YPT; q++) ys[tid + q * NT] = yacc[q];
         cta_sync<NW>();
 
-        // ---- Cholesky, right-looking with 4-column panels; thread t owns rows t + q*NT
-        bool bad = false;
-        for (int j0 = 0; j0 < KP; j0 += 4) {
-            const float a00 = As[(j0 + 0) * LDA + j0];
-            const float a10 = As[(j0 + 1) * LDA + j0], a11 = As[(j0 + 1) * LDA + j0 + 1];
-            const float a20 = As[(j0 + 2) * LDA + j0], a21 = As[(j0 + 2) * LDA + j0 + 1],
-                        a22 = As[(j0 + 2) * LDA + j0 + 2];
-            const float a30 = As[(j0 + 3) * LDA + j0], a31 = As[(j0 + 3) * LDA + j0 + 1],
-                        a32 = As[(j0 + 3) * LDA + j0 + 2], a33 = As[(j0 + 3) * LDA + j0 + 3];
-            const float l00 = sqrtf(a00), i0 = 1.0f / l00;
-            const float l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
-            const float d1 = a11 - l10 * l10;
-            const float l11 = sqrtf(d1), i1 = 1.0f / l11;
-            const float l21 = (a21 - l20 * l10) * i1, l31 = (a31 - l30 * l10) * i1;
-            const float d2 = a22 - l20 * l20 - l21 * l21;
-            const float l22 = sqrtf(d2), i2 = 1.0f / l22;
-            const float l32 = (a32 - l30 * l20 - l31 * l21) * i2;
-            const float d3 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
-            const float l33 = sqrtf(d3), i3 = 1.0f / l33;
-            bad |= !(a00 > 0.0f && d1 > 0.0f && d2 > 0.0f && d3 > 0.0f);
-            cta_sync<NW>();  // all reads of the diagonal block precede its overwrite
-
-            float x[C::RPT][4];
-#pragma unroll
-            for (int q = 0; q < C::RPT; q++) {
-                const int i = tid + q * NT;
-                x[q][0] = x[q][1] = x[q][2] = x[q][3] = 0.0f;
-                if (i >= j0 + 4) {
-                    float4 ar = *reinterpret_cast<const float4 *>(As + i * LDA + j0);
-                    const float x0 = ar.x * i0;
-                    const float x1 = (ar.y - x0 * l10) * i1;
-                    const float x2 = (ar.z - x0 * l20 - x1 * l21) * i2;
-                    const float x3 = (ar.w - x0 * l30 - x1 * l31 - x2 * l32) * i3;
-                    x[q][0] = x0, x[q][1] = x1, x[q][2] = x2, x[q][3] = x3;
-                    *reinterpret_cast<float4 *>(As + i * LDA + j0) = make_float4(x0, x1, x2, x3);
-                } else if (i >= j0) {
-                    const int r = i - j0;
-                    float4 lr = r == 0   ? make_float4(l00, 0.f, 0.f, 0.f)
-                                : r == 1 ? make_float4(l10, l11, 0.f, 0.f)
-                                : r == 2 ? make_float4(l20, l21, l22, 0.f)
-                                         : make_float4(l30, l31, l32, l33);
-                    *reinterpret_cast<float4 *>(As + i * LDA + j0) = lr;
-                    dinv[i] = r == 0 ? i0 : r == 1 ? i1 : r == 2 ? i2 : i3;
-                }
-            }
-            cta_sync<NW>();
-            for (int cc = j0 + 4; cc < KP; cc += 4) {
-                const float4 L0 = *reinterpret_cast<const float4 *>(As + (cc + 0) * LDA + j0);
-                const float4 L1 = *reinterpret_cast<const float4 *>(As + (cc + 1) * LDA + j0);
-                const float4 L2 = *reinterpret_cast<const float4 *>(As + (cc + 2) * LDA + j0);
-                const float4 L3 = *reinterpret_cast<const float4 *>(As + (cc + 3) * LDA + j0);
-#pragma unroll
-                for (int q = 0; q < C::RPT; q++) {
-                    const int i = tid + q * NT;
-                    if (i >= cc) {
-                        float4 av = *reinterpret_cast<float4 *>(As + i * LDA + cc);
-                        av.x -= x[q][0] * L0.x + x[q][1] * L0.y + x[q][2] * L0.z + x[q][3] * L0.w;
-                        av.y -= x[q][0] * L1.x + x[q][1] * L1.y + x[q][2] * L1.z + x[q][3] * L1.w;
-                        av.z -= x[q][0] * L2.x + x[q][1] * L2.y + x[q][2] * L2.z + x[q][3] * L2.w;
-                        av.w -= x[q][0] * L3.x + x[q][1] * L3.y + x[q][2] * L3.z + x[q][3] * L3.w;
-                        *reinterpret_cast<float4 *>(As + i * LDA + cc) = av;
-                    }
-                }
-            }
-            cta_sync<NW>();
-        }
-        // forward substitution L z = y (column oriented)
-        for (int j = 0; j < KP; j++) {
-            const float zj = ys[j] * dinv[j];
-            cta_sync<NW>();
-#pragma unroll
-            for (int q = 0; q < C::RPT; q++) {
-                const int i = tid + q * NT;
-                if (i > j)
-                    ys[i] -= As[i * LDA + j] * zj;
-                else if (i == j)
-                    ys[i] = zj;
-            }
-            cta_sync<NW>();
-        }
-        // back substitution L^T x = z
-        for (int j = KP - 1; j >= 0; j--) {
-            const float xj = ys[j] * dinv[j];
-            cta_sync<NW>();
-#pragma unroll
-            for (int q = 0; q < C::RPT; q++) {
-                const int i = tid + q * NT;
-                if (i < j)
-                    ys[i] -= As[j * LDA + i] * xj;
-                else if (i == j)
-                    ys[i] = xj;
-            }
-            cta_sync<NW>();
-        }
-
-        // ---- write the row, accumulate |x - x_old|^2
-        bad = __syncthreads_or(bad);
-        if (bad) {
-            if (tid == 0) atomicCAS(a.d_status, 0, row + 1);
-        } else {
-            float d2 = 0.0f;
-#pragma unroll
-            for (int q = 0; q < C::RPT; q++) {
-                const int i = tid + q * NT;
-                if (i < k) {
-                    const float xn = ys[i];
-                    const float d = xn - thisrow[i];
-                    d2 = fmaf(d, d, d2);
-                    thisrow[i] = xn;
-                    for (int r = 0; r < a.n_replicas; r++)
-                        a.d_replicas[r][(size_t)(a.replica_row0 + row) * k + i] = xn;
-                }
-            }
-            d2 = warp_sum(d2);
-            if (lane == 0 && d2 != 0.0f) atomicAdd(a.d_sqdelta, (double)d2);
-        }
+        // ---- Cholesky + triangular solves in shared memory, then write the row
+        const bool bad = chol_solve<KP, NW>(As, ys, dinv, tid);
+        write_row<KP, NW>(a, row, thisrow, ys, tid, bad);
         // the next chunk's bulk copies (async proxy) overwrite this buffer
         fence_proxy_async();
         __syncthreads();
@@ -555,6 +433,8 @@ __global__ void otor_reduce_kernel(const float *__restrict__ partial, int nblock
     if (i == j) s += reg;
     out[e] = s;
 }
+
+int launch_als_tc(const lk_als_args &a, cudaStream_t st);  // als_tc.cu
 
 static int pad_features(int k) { return k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : -1; }
 
@@ -694,6 +574,9 @@ int lk_als_half_epoch(const lk_als_args *args, void *stream)
     if (a.n_split_rows > 0)
         LK_CUDA_TRY(cudaMemsetAsync(a.d_split_counters, 0, sizeof(int32_t) * a.n_split_rows, st));
     if (a.other_dtype == LK_DTYPE_F32) return dispatch_k<float>(a, st);
+    // k = 64, bf16 rows, unweighted / uniformly weighted Gram: tensor-core kernel (als_tc.cu)
+    const int rc = launch_als_tc(a, st);
+    if (rc <= 0) return rc;
     return dispatch_k<__nv_bfloat16>(a, st);
 }
 

@@ -1,0 +1,473 @@
+// als_tc.cu — ALS half-epoch with the Gram matrix on the 5th-gen tensor cores.
+//
+// Same contract as als_half_kernel (als_kernels.cu; reference
+// src/accel/als/implicit.rs:87-125, explicit.rs:80-119) for the configuration the
+// headline metric is quoted on: k = 64, the opposite factor table gathered as
+// bf16 rows, and a Gram that is an unweighted (explicit) or uniformly weighted
+// (implicit, use_ratings=False: every confidence equals `weight`) contraction:
+//
+//      G = M^T M            M = other[cols, :]   (n x 64, bf16, 128 B per row)
+//      implicit: A = OtOr + v*G      y = sum_j (v_j + 1) m_j
+//      explicit: A = G + reg*n*I     y = sum_j v_j m_j
+//
+// G is a variable-length SYRK: D[64x64] += A[64 x K] * B[K x 64] with A = M^T and
+// B = M.  Both operands are the *same* shared-memory tile read MN-major (the
+// feature index is the contiguous one), so one gathered row of 64 bf16 is exactly
+// one 128-byte row of the canonical SWIZZLE_128B MN-major layout: the gather is
+// eight 16-byte cp.async per row with the chunk index XORed by (row & 7) — no
+// transposes, no repacking.  One tcgen05.mma (kind::f16, M=64, N=64, K=16) eats
+// 16 gathered rows (65,536 MACs); accumulation is fp32 in TMEM, and because the
+// operands *are* bf16 the products are exact — parity is against the oracle that
+// rounds the gathered rows to bf16 the same way.
+//
+// CTA = 4 warps working in lock-step groups of 4 row-chunks:
+//   phase 1  each warp gathers its own chunk through a 4-stage cp.async ring,
+//            lane 0 issues the MMAs into the warp's TMEM accumulator and commits
+//            them to mbarriers (stage free / accumulator full); the right-hand
+//            side y is accumulated on the SIMT side from the same tile;
+//   phase 2  all four warps drain the accumulators (a warp can only read its own
+//            quarter of the TMEM lanes: for M=64 rows 16w..16w+15 of *every*
+//            accumulator) into the per-warp shared-memory systems, adding OtOr or
+//            reg*n*I; chunks of split rows go to their partial slot instead and
+//            the last part to arrive reduces the slots in order (deterministic);
+//   phase 3  each warp factors and solves its own 64x64 system (als_common.cuh).
+// Two M=64 accumulators share 64 TMEM columns (lanes 0-15 / 16-31 of every
+// quarter, the "interleaved" allocation), so a CTA needs 128 columns.
+
+#include "als_common.cuh"
+
+namespace lk {
+
+namespace tc {
+constexpr int KP = 64;
+constexpr int WARPS = 4;
+constexpr int NT = WARPS * 32;
+constexpr int STAGE_ROWS = 32;
+constexpr int NSTAGE = 4;
+constexpr int ROW_BYTES = KP * 2;
+constexpr int STAGE_BYTES = STAGE_ROWS * ROW_BYTES;  // 4096
+constexpr int LDA = KP + 4;
+constexpr int WARP_BYTES = KP * LDA * 4;  // 17408 = 17 * 1024 >= NSTAGE * STAGE_BYTES
+static_assert(WARP_BYTES >= NSTAGE * STAGE_BYTES && WARP_BYTES % 1024 == 0, "stage ring must fit, 1 KB aligned");
+constexpr int TMEM_COLS = 128;
+constexpr int SLOTF = KP * KP + KP;
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + WARPS * WARP_BYTES + 2 * WARPS * KP * 4 +
+                           (WARPS * NSTAGE + WARPS) * 8 + 16 + 64 * 4;
+
+// instruction descriptor: D=f32, A=B=bf16, both MN-major, N=64, M=64 (mma_sm100_desc.hpp InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) |
+                           ((64u >> 4) << 24);
+// shared-memory descriptor, high part: SBO = 1024 B between 8-row groups along K, version 1, SWIZZLE_128B
+constexpr uint64_t DESC_HI = (uint64_t(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+constexpr uint64_t DESC_LBO = uint64_t(1) << 16;  // single 64-wide MN atom: leading offset unused
+}  // namespace tc
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16_64x64x16(uint32_t tmem_d, uint64_t desc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %3, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %1, %2, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc), "r"(tc::IDESC), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 64 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t (&r)[64])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// interleave != 0: two accumulators share 64 columns (TMEM lanes 0-15 / 16-31 of each
+// quarter), 128 columns per CTA; interleave == 0: one accumulator per 64 columns, 256 per CTA.
+template <int MODE>
+__global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const int interleave)
+{
+    using namespace tc;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    unsigned char *wreg = base + warp * WARP_BYTES;  // this warp's stage ring, later its 64x68 system
+    float *As = reinterpret_cast<float *>(wreg);
+    float *ys_all = reinterpret_cast<float *>(base + WARPS * WARP_BYTES);
+    float *ys = ys_all + warp * KP;
+    float *dinv = ys_all + WARPS * KP + warp * KP;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ys_all + 2 * WARPS * KP);
+    uint64_t *stage_free = bars + warp * NSTAGE;  // [NSTAGE] of this warp
+    uint64_t *acc_full = bars + WARPS * NSTAGE;   // [WARPS]
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(acc_full + WARPS);
+    int *s_misc = reinterpret_cast<int *>(s_tmem + 4);  // [0] group, then per-chunk metadata [8 + 8*c ...]
+
+    const __nv_bfloat16 *__restrict__ other = reinterpret_cast<const __nv_bfloat16 *>(a.d_other);
+    constexpr int k = KP;
+
+    if (tid == 0) {
+        for (int i = 0; i < WARPS * NSTAGE + WARPS; i++) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"((uint32_t)(interleave ? TMEM_COLS : 2 * TMEM_COLS))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    // accumulator of warp w: columns 64*(w/2), lanes 16*(w%2) of every 32-lane quarter
+    const uint32_t my_acc = interleave
+                                ? tmem_base + ((uint32_t)((warp & 1) * 16) << 16) + (uint32_t)((warp >> 1) * 64)
+                                : tmem_base + (uint32_t)(warp * 64);
+
+    uint32_t free_par = 0;  // bit s: parity of the number of commits issued on stage_free[s]
+    uint32_t full_par = 0;  // bit c: parity of the number of commits seen on acc_full[c]
+
+    for (;;) {
+        if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);
+        __syncthreads();
+        const int64_t g = s_misc[0];
+        __syncthreads();
+        if (g * WARPS >= a.n_chunks) break;
+        const int64_t ci = g * WARPS + warp;
+        const bool active = ci < a.n_chunks;
+        int row = -1, begin = 0, len = 0, nparts = 1, slot0 = 0, part = 0, split_idx = 0;
+        if (active) {
+            const int4 c0 = __ldg(reinterpret_cast<const int4 *>(a.d_chunks) + 2 * ci);
+            const int4 c1 = __ldg(reinterpret_cast<const int4 *>(a.d_chunks) + 2 * ci + 1);
+            row = c0.x, begin = c0.y, len = c0.z, nparts = c0.w;
+            slot0 = c1.x, part = c1.y, split_idx = c1.z;
+        }
+        const bool has_gram = active && len > 0;
+        int n_row = 0;
+        if (active) n_row = __ldg(a.d_indptr + row + 1) - __ldg(a.d_indptr + row);
+        if (lane == 0) {
+            int *m = s_misc + 8 + 8 * warp;
+            m[0] = has_gram ? 1 : 0;
+            m[1] = nparts;
+            m[2] = slot0 + part;
+            m[3] = n_row;
+        }
+
+        // ------------------------------------------------------------------
+        // phase 1: gather -> tcgen05.mma, y on the side
+        // ------------------------------------------------------------------
+        float y0 = 0.0f, y1 = 0.0f;  // features 2*lane, 2*lane+1
+        if (has_gram) {
+            const int n_it = (len + STAGE_ROWS - 1) / STAGE_ROWS;
+            const int32_t *cols = a.d_cols + begin;
+            const float *vals = a.d_vals + begin;
+            float vst[NSTAGE];  // value of row (it*32 + lane) for the stage in buffer s
+#pragma unroll
+            for (int s = 0; s < NSTAGE; s++) vst[s] = 0.0f;
+
+            auto fetch = [&](int it, int &c, float &v) {
+                const int idx = it * STAGE_ROWS + lane;
+                if (it < n_it && idx < len) {
+                    c = __ldg(cols + idx);
+                    v = __ldg(vals + idx);
+                } else {
+                    c = 0;
+                    v = 0.0f;
+                }
+            };
+            // issue the gather of stage `it` (rows it*32 ..) into ring buffer s; c = this lane's column index
+            auto issue = [&](int it, int s, int c) {
+                if (it < n_it) {
+                    const int nrows = min(STAGE_ROWS, len - it * STAGE_ROWS);
+                    const int npad = (nrows + 15) & ~15;
+                    const uint32_t sbase = smem_u32(wreg + s * STAGE_BYTES);
+                    const int chunk = lane & 7;
+#pragma unroll
+                    for (int t = 0; t < STAGE_ROWS / 4; t++) {
+                        const int r = 4 * t + (lane >> 3);
+                        const int cr = __shfl_sync(FULL, c, r);
+                        const uint32_t dst = sbase + r * ROW_BYTES + ((chunk ^ (r & 7)) << 4);
+                        if (r < nrows) {
+                            cp_async16(dst, other + (size_t)cr * k + chunk * 8);
+                        } else if (r < npad) {
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+                        }
+                    }
+                }
+                cp_async_commit();
+            };
+
+            int cpre[NSTAGE - 1];
+            float vpre[NSTAGE - 1];
+#pragma unroll
+            for (int j = 0; j < NSTAGE - 1; j++) fetch(j, cpre[j], vpre[j]);
+#pragma unroll
+            for (int j = 0; j < NSTAGE - 1; j++) {
+                issue(j, j, cpre[j]);
+                vst[j] = vpre[j];
+            }
+            int cnext;
+            float vnext;
+            fetch(NSTAGE - 1, cnext, vnext);
+
+            for (int it0 = 0; it0 < n_it; it0 += NSTAGE) {
+#pragma unroll
+                for (int s = 0; s < NSTAGE; s++) {
+                    const int it = it0 + s;
+                    if (it < n_it) {
+                        // 1. refill the buffer that stage it-1 used (stage it+NSTAGE-1 goes there)
+                        const int sj = (s + NSTAGE - 1) % NSTAGE;  // constant after unrolling
+                        const int j = it + NSTAGE - 1;
+                        if (j < n_it && j >= NSTAGE) {
+                            // the MMAs of iteration it-1 were the last commit on this buffer
+                            mbar_wait(&stage_free[sj], ((free_par >> sj) & 1u) ^ 1u);
+                        }
+                        issue(j, sj, cnext);
+                        if (j < n_it) vst[sj] = vnext;
+                        fetch(j + 1, cnext, vnext);
+                        // 2. stage `it` has landed
+                        cp_async_wait<NSTAGE - 1>();
+                        fence_proxy_async();
+                        __syncwarp();
+                        const int nrows = min(STAGE_ROWS, len - it * STAGE_ROWS);
+                        // 3. tensor cores: 16 rows per instruction
+                        if (lane == 0) {
+                            tmem_fence_after();
+                            const uint32_t sbase = smem_u32(wreg + s * STAGE_BYTES);
+                            const int nk = (nrows + 15) >> 4;
+                            for (int kk = 0; kk < nk; kk++) {
+                                const uint64_t desc =
+                                    DESC_HI | DESC_LBO | (uint64_t)(((sbase + kk * 2048) >> 4) & 0x3fffu);
+                                umma_bf16_64x64x16(my_acc, desc, (it > 0 || kk > 0) ? 1u : 0u);
+                            }
+                            umma_commit(&stage_free[s]);
+                            if (it == n_it - 1) umma_commit(&acc_full[warp]);
+                        }
+                        free_par ^= (1u << s);
+                        // 4. right-hand side from the same tile: lane owns features 2*lane, 2*lane+1
+                        {
+                            const unsigned char *st = wreg + s * STAGE_BYTES;
+                            const int chunk = lane >> 2, within = (lane & 3) * 4;
+                            for (int r = 0; r < nrows; r++) {
+                                float w = __shfl_sync(FULL, vst[s], r);
+                                if constexpr (MODE == LK_ALS_IMPLICIT) w += 1.0f;
+                                const uint32_t two = *reinterpret_cast<const uint32_t *>(
+                                    st + r * ROW_BYTES + ((chunk ^ (r & 7)) << 4) + within);
+                                y0 = fmaf(__uint_as_float(two << 16), w, y0);
+                                y1 = fmaf(__uint_as_float(two & 0xffff0000u), w, y1);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            cp_async_wait<0>();
+        }
+        __syncthreads();  // every warp has issued its MMAs; chunk metadata is visible
+
+        // ------------------------------------------------------------------
+        // phase 2: drain the accumulators into the per-warp systems
+        // ------------------------------------------------------------------
+        int gram[WARPS], parts[WARPS], slotc[WARPS], nrowc[WARPS];
+#pragma unroll
+        for (int c = 0; c < WARPS; c++) {
+            const int *m = s_misc + 8 + 8 * c;
+            gram[c] = m[0], parts[c] = m[1], slotc[c] = m[2], nrowc[c] = m[3];
+        }
+#pragma unroll
+        for (int c = 0; c < WARPS; c++) {
+            if (gram[c]) {
+                full_par ^= (1u << c);
+                mbar_wait(&acc_full[c], ((full_par >> c) & 1u) ^ 1u);
+            }
+        }
+        tmem_fence_after();
+        const int n_loads = interleave ? 2 : 4;
+        for (int p = 0; p < n_loads; p++) {
+            if (interleave ? !(gram[2 * p] || gram[2 * p + 1]) : !gram[p]) continue;
+            uint32_t r[64];
+            tmem_ld_32x32b_x64(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(p * 64), r);
+            const int c = interleave ? 2 * p + (lane >> 4) : p;
+            const int gi = 16 * warp + (lane & 15);  // Gram row held by this lane
+            if (gram[c] && (interleave || lane < 16)) {
+                if (parts[c] == 1) {
+                    float *Ac = reinterpret_cast<float *>(base + c * WARP_BYTES) + gi * LDA;
+                    if constexpr (MODE == LK_ALS_IMPLICIT) {
+                        const float v = a.uniform_val;
+                        const float4 *ot = reinterpret_cast<const float4 *>(a.d_otor + gi * k);
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            const float4 o = __ldg(ot + q);
+                            float4 t;
+                            t.x = fmaf(v, __uint_as_float(r[4 * q + 0]), o.x);
+                            t.y = fmaf(v, __uint_as_float(r[4 * q + 1]), o.y);
+                            t.z = fmaf(v, __uint_as_float(r[4 * q + 2]), o.z);
+                            t.w = fmaf(v, __uint_as_float(r[4 * q + 3]), o.w);
+                            *reinterpret_cast<float4 *>(Ac + 4 * q) = t;
+                        }
+                    } else {
+                        const float regn = a.reg * (float)nrowc[c];
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            float4 t = make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                            if (gi >> 2 == q) {
+                                if ((gi & 3) == 0) t.x += regn;
+                                if ((gi & 3) == 1) t.y += regn;
+                                if ((gi & 3) == 2) t.z += regn;
+                                if ((gi & 3) == 3) t.w += regn;
+                            }
+                            *reinterpret_cast<float4 *>(Ac + 4 * q) = t;
+                        }
+                    }
+                } else {
+                    float *slot = a.d_partials + (size_t)slotc[c] * SLOTF + gi * KP;
+#pragma unroll
+                    for (int q = 0; q < 16; q++)
+                        __stcg(reinterpret_cast<float4 *>(slot) + q,
+                               make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                           __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+                }
+            }
+        }
+        tmem_fence_before();
+        // right-hand side of this warp's chunk
+        if (has_gram) {
+            if (nparts == 1) {
+                ys[2 * lane] = y0;
+                ys[2 * lane + 1] = y1;
+            } else {
+                float *slot = a.d_partials + (size_t)(slot0 + part) * SLOTF + KP * KP;
+                __stcg(reinterpret_cast<float2 *>(slot) + lane, make_float2(y0, y1));
+            }
+        }
+        __threadfence();
+        __syncthreads();
+
+        // split rows: the last part to arrive sums the slots in order
+        bool solve = has_gram && nparts == 1;
+        if (active && nparts > 1) {
+            int last = 0;
+            if (lane == 0) last = (atomicAdd(a.d_split_counters + split_idx, 1) == nparts - 1) ? 1 : 0;
+            last = __shfl_sync(FULL, last, 0);
+            if (last) {
+                __threadfence();
+                const float regn = a.reg * (float)n_row;
+                for (int idx = lane; idx < KP * KP; idx += 32) {
+                    float s = 0.0f;
+                    for (int p = 0; p < nparts; p++) s += __ldcg(a.d_partials + (size_t)(slot0 + p) * SLOTF + idx);
+                    const int gi = idx >> 6, gc = idx & 63;
+                    if constexpr (MODE == LK_ALS_IMPLICIT)
+                        s = fmaf(a.uniform_val, s, __ldg(a.d_otor + idx));
+                    else if (gi == gc)
+                        s += regn;
+                    As[gi * LDA + gc] = s;
+                }
+                for (int f = lane; f < KP; f += 32) {
+                    float s = 0.0f;
+                    for (int p = 0; p < nparts; p++)
+                        s += __ldcg(a.d_partials + (size_t)(slot0 + p) * SLOTF + KP * KP + f);
+                    ys[f] = s;
+                }
+                solve = true;
+            }
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------------
+        // phase 3: per-warp Cholesky solve and write-back
+        // ------------------------------------------------------------------
+        if (active) {
+            float *thisrow = a.d_this + (size_t)row * k;
+            if (solve) {
+                const bool bad = chol_solve<KP, 1>(As, ys, dinv, lane);
+                write_row<KP, 1>(a, row, thisrow, ys, lane, bad);
+            } else if (len == 0 && nparts == 1) {
+                // empty row: x = 0, no delta (implicit.rs:98-101)
+                for (int i = lane; i < k; i += 32) {
+                    thisrow[i] = 0.0f;
+                    for (int rr = 0; rr < a.n_replicas; rr++)
+                        a.d_replicas[rr][(size_t)(a.replica_row0 + row) * k + i] = 0.0f;
+                }
+            }
+        }
+        __syncthreads();  // the systems alias the stage rings of the next group
+    }
+
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)(interleave ? tc::TMEM_COLS : 2 * tc::TMEM_COLS))
+                     : "memory");
+    }
+}
+
+// returns LK_OK when the tensor-core kernel took the launch, 1 when the caller
+// should fall back to the SIMT kernel
+int launch_als_tc(const lk_als_args &a, cudaStream_t st)
+{
+    if (a.k != tc::KP || a.other_dtype != LK_DTYPE_BF16) return 1;
+    if (a.mode == LK_ALS_IMPLICIT && !a.vals_uniform) return 1;
+    if (reinterpret_cast<uintptr_t>(a.d_other) % 16 != 0) return 1;
+    if (const char *e = getenv("LK_ALS_TC"))
+        if (e[0] == '0') return 1;
+    int interleave = 1;
+    if (const char *e = getenv("LK_ALS_TC_INTERLEAVE")) interleave = e[0] != '0';
+    const int cols = interleave ? tc::TMEM_COLS : 2 * tc::TMEM_COLS;
+    const int smem = tc::SMEM_BYTES;
+    int64_t groups = (a.n_chunks + tc::WARPS - 1) / tc::WARPS;
+    int occ = 0;
+    if (a.mode == LK_ALS_IMPLICIT) {
+        auto kern = als_tc_kernel<LK_ALS_IMPLICIT>;
+        LK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tc::NT, smem));
+        occ = std::max(1, std::min(occ, 512 / cols));
+        const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
+        kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave);
+    } else {
+        auto kern = als_tc_kernel<LK_ALS_EXPLICIT>;
+        LK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tc::NT, smem));
+        occ = std::max(1, std::min(occ, 512 / cols));
+        const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
+        kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave);
+    }
+    LK_CUDA_TRY(cudaGetLastError());
+    return LK_OK;
+}
+
+}  // namespace lk

@@ -71,6 +71,8 @@ class ALSHalfPlan:
     work_counter: torch.Tensor
     sqdelta: torch.Tensor
     status: torch.Tensor
+    vals_uniform: bool = False
+    uniform_val: float = 0.0
 
     @classmethod
     def create(cls, matrix: DeviceCSR, k: int, chunk_nnz: int = DEFAULT_CHUNK_NNZ) -> "ALSHalfPlan":
@@ -92,7 +94,13 @@ class ALSHalfPlan:
         if ns.value > 0:
             partials = torch.empty(nslot.value * slot_f, dtype=torch.float32, device=dev)
             counters = torch.zeros(ns.value, dtype=torch.int32, device=dev)
+        uniform, uval = False, 0.0
+        if matrix.nnz > 0:
+            lo, hi = torch.aminmax(matrix.values)
+            uniform, uval = bool(lo == hi), float(lo)
         return cls(
+            vals_uniform=uniform,
+            uniform_val=uval,
             matrix=matrix,
             k=k,
             chunk_nnz=chunk_nnz,
@@ -188,6 +196,8 @@ def als_half_epoch(
     a.d_work_counter = ptr(plan.work_counter)
     a.d_sqdelta = ptr(plan.sqdelta)
     a.d_status = ptr(plan.status)
+    a.vals_uniform = 1 if plan.vals_uniform else 0
+    a.uniform_val = plan.uniform_val
     check(lib().lk_als_half_epoch(C.byref(a), stream_ptr()), "lk_als_half_epoch")
 
 
