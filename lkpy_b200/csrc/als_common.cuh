@@ -16,13 +16,26 @@ __device__ __forceinline__ void cta_sync()
         __syncthreads();
 }
 
+// 1/sqrt(x) to f32 rounding: MUFU.RSQ seed + one Newton step (the IEEE sqrtf +
+// divide pair costs ~4x the issue slots and sits on every panel's critical path)
+__device__ __forceinline__ float rsqrt_nr(float x)
+{
+    const float r = rsqrtf(x);
+    const float h = 0.5f * x;
+    return r * fmaf(-h * r, r, 1.5f);
+}
+
 // Solve A x = y for a KP x KP SPD matrix held row-major in shared memory with
 // row stride KP+4 (lower triangle used), rhs in ys, scratch dinv[KP].  Executed
 // by NW warps together (NW == 1: one warp, only __syncwarp).  Thread t owns rows
-// t + q*32*NW.  On return ys holds x; the result is true when a pivot was not
-// positive (LAPACK info != 0).  Right-looking, 4-column panels: every thread
-// factors the 4x4 diagonal block redundantly from broadcast reads, solves the
-// panel entries of its own rows, then updates the trailing matrix in 4x4 tiles.
+// t + q*32*NW and keeps their right-hand-side entries in registers.  On return
+// ys holds x; the result is true when a pivot was not positive (LAPACK info != 0).
+//
+// Right-looking factorisation with 4-column panels: every thread factors the 4x4
+// diagonal block redundantly from broadcast reads, solves the panel entries of its
+// own rows, applies the panel to its right-hand side (the forward substitution is
+// fused into the factorisation), then updates the trailing matrix in 4x4 tiles.
+// The back substitution L^T x = z runs panel by panel from the bottom.
 template <int KP, int NW>
 __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, const int tid)
 {
@@ -31,6 +44,10 @@ __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, co
     constexpr int RPT = KP / NT;
     static_assert(RPT >= 1, "at most KP threads may share one system");
     bool bad = false;
+    float yv[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; q++) yv[q] = ys[tid + q * NT];
+
     for (int j0 = 0; j0 < KP; j0 += 4) {
         const float a00 = As[(j0 + 0) * LDA + j0];
         const float a10 = As[(j0 + 1) * LDA + j0], a11 = As[(j0 + 1) * LDA + j0 + 1];
@@ -38,18 +55,24 @@ __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, co
                     a22 = As[(j0 + 2) * LDA + j0 + 2];
         const float a30 = As[(j0 + 3) * LDA + j0], a31 = As[(j0 + 3) * LDA + j0 + 1],
                     a32 = As[(j0 + 3) * LDA + j0 + 2], a33 = As[(j0 + 3) * LDA + j0 + 3];
-        const float l00 = sqrtf(a00), i0 = 1.0f / l00;
+        const float y0 = ys[j0], y1 = ys[j0 + 1], y2 = ys[j0 + 2], y3 = ys[j0 + 3];
+        const float i0 = rsqrt_nr(a00), l00 = a00 * i0;
         const float l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
         const float d1 = a11 - l10 * l10;
-        const float l11 = sqrtf(d1), i1 = 1.0f / l11;
+        const float i1 = rsqrt_nr(d1), l11 = d1 * i1;
         const float l21 = (a21 - l20 * l10) * i1, l31 = (a31 - l30 * l10) * i1;
         const float d2 = a22 - l20 * l20 - l21 * l21;
-        const float l22 = sqrtf(d2), i2 = 1.0f / l22;
+        const float i2 = rsqrt_nr(d2), l22 = d2 * i2;
         const float l32 = (a32 - l30 * l20 - l31 * l21) * i2;
         const float d3 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
-        const float l33 = sqrtf(d3), i3 = 1.0f / l33;
+        const float i3 = rsqrt_nr(d3), l33 = d3 * i3;
         bad |= !(a00 > 0.0f && d1 > 0.0f && d2 > 0.0f && d3 > 0.0f);
-        cta_sync<NW>();  // all reads of the diagonal block precede its overwrite
+        // forward substitution for the four pivot rows
+        const float z0 = y0 * i0;
+        const float z1 = (y1 - l10 * z0) * i1;
+        const float z2 = (y2 - l20 * z0 - l21 * z1) * i2;
+        const float z3 = (y3 - l30 * z0 - l31 * z1 - l32 * z2) * i3;
+        cta_sync<NW>();  // all reads of the diagonal block / pivot rhs precede their overwrite
 
         float x[RPT][4];
 #pragma unroll
@@ -64,6 +87,8 @@ __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, co
                 const float x3 = (ar.w - x0 * l30 - x1 * l31 - x2 * l32) * i3;
                 x[q][0] = x0, x[q][1] = x1, x[q][2] = x2, x[q][3] = x3;
                 *reinterpret_cast<float4 *>(As + i * LDA + j0) = make_float4(x0, x1, x2, x3);
+                yv[q] -= x0 * z0 + x1 * z1 + x2 * z2 + x3 * z3;
+                if (i < j0 + 8) ys[i] = yv[q];  // pivot rows of the next panel
             } else if (i >= j0) {
                 const int r = i - j0;
                 float4 lr = r == 0   ? make_float4(l00, 0.f, 0.f, 0.f)
@@ -72,6 +97,7 @@ __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, co
                                      : make_float4(l30, l31, l32, l33);
                 *reinterpret_cast<float4 *>(As + i * LDA + j0) = lr;
                 dinv[i] = r == 0 ? i0 : r == 1 ? i1 : r == 2 ? i2 : i3;
+                yv[q] = r == 0 ? z0 : r == 1 ? z1 : r == 2 ? z2 : z3;
             }
         }
         cta_sync<NW>();
@@ -82,6 +108,7 @@ __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, co
             const float4 L3 = *reinterpret_cast<const float4 *>(As + (cc + 3) * LDA + j0);
 #pragma unroll
             for (int q = 0; q < RPT; q++) {
+                if (q * NT + NT - 1 < cc) continue;  // this whole row group is above the tile (uniform)
                 const int i = tid + q * NT;
                 if (i >= cc) {
                     float4 av = *reinterpret_cast<float4 *>(As + i * LDA + cc);
@@ -95,34 +122,41 @@ __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, co
         }
         cta_sync<NW>();
     }
-    // forward substitution L z = y (column oriented)
-    for (int j = 0; j < KP; j++) {
-        const float zj = ys[j] * dinv[j];
+
+    // back substitution L^T x = z, four unknowns at a time from the bottom; yv holds z
+#pragma unroll
+    for (int q = 0; q < RPT; q++) {
+        const int i = tid + q * NT;
+        if (i >= KP - 4) ys[i] = yv[q];
+    }
+    cta_sync<NW>();
+    for (int j0 = KP - 4; j0 >= 0; j0 -= 4) {
+        const float l10 = As[(j0 + 1) * LDA + j0];
+        const float l20 = As[(j0 + 2) * LDA + j0], l21 = As[(j0 + 2) * LDA + j0 + 1];
+        const float l30 = As[(j0 + 3) * LDA + j0], l31 = As[(j0 + 3) * LDA + j0 + 1],
+                    l32 = As[(j0 + 3) * LDA + j0 + 2];
+        const float x3 = ys[j0 + 3] * dinv[j0 + 3];
+        const float x2 = (ys[j0 + 2] - l32 * x3) * dinv[j0 + 2];
+        const float x1 = (ys[j0 + 1] - l21 * x2 - l31 * x3) * dinv[j0 + 1];
+        const float x0 = (ys[j0] - l10 * x1 - l20 * x2 - l30 * x3) * dinv[j0];
         cta_sync<NW>();
 #pragma unroll
         for (int q = 0; q < RPT; q++) {
             const int i = tid + q * NT;
-            if (i > j)
-                ys[i] -= As[i * LDA + j] * zj;
-            else if (i == j)
-                ys[i] = zj;
+            if (i < j0) {
+                yv[q] -= As[(j0 + 0) * LDA + i] * x0 + As[(j0 + 1) * LDA + i] * x1 +
+                         As[(j0 + 2) * LDA + i] * x2 + As[(j0 + 3) * LDA + i] * x3;
+                if (i >= j0 - 4) ys[i] = yv[q];  // pivot rows of the next (upper) panel
+            } else if (i < j0 + 4) {
+                const int r = i - j0;
+                yv[q] = r == 0 ? x0 : r == 1 ? x1 : r == 2 ? x2 : x3;
+            }
         }
         cta_sync<NW>();
     }
-    // back substitution L^T x = z
-    for (int j = KP - 1; j >= 0; j--) {
-        const float xj = ys[j] * dinv[j];
-        cta_sync<NW>();
 #pragma unroll
-        for (int q = 0; q < RPT; q++) {
-            const int i = tid + q * NT;
-            if (i < j)
-                ys[i] -= As[j * LDA + i] * xj;
-            else if (i == j)
-                ys[i] = xj;
-        }
-        cta_sync<NW>();
-    }
+    for (int q = 0; q < RPT; q++) ys[tid + q * NT] = yv[q];
+    cta_sync<NW>();
     return bad;
 }
 
