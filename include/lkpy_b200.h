@@ -119,6 +119,7 @@ typedef struct lk_als_args {
     int32_t vals_uniform;    /* 1 when every d_vals entry equals uniform_val (implicit feedback without
                                 ratings): lets the Gram run on the tensor cores as v * M^T M */
     float uniform_val;
+    unsigned long long *d_prof; /* optional [8] per-phase SM-cycle counters (diagnostics), or NULL */
 } lk_als_args;
 
 LK_API int lk_als_half_epoch(const lk_als_args *args, void *stream);

@@ -57,6 +57,7 @@ class LkAlsArgs(C.Structure):
         ("d_status", vp),
         ("vals_uniform", C.c_int32),
         ("uniform_val", C.c_float),
+        ("d_prof", vp),
     ]
 
 

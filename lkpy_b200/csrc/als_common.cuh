@@ -101,6 +101,11 @@ __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, co
             }
         }
         cta_sync<NW>();
+        // Trailing update A[i][cc..cc+3] -= L[i][j0..j0+3] . L[cc..cc+3][j0..j0+3]^T for every row i
+        // and every 4-column tile right of the panel.  Rows above a tile (i < cc) only touch the
+        // never-read upper triangle and pivot rows carry x = 0, so the update is applied without a
+        // per-lane branch; tiles are independent, so two are kept in flight for latency.
+#pragma unroll 2
         for (int cc = j0 + 4; cc < KP; cc += 4) {
             const float4 L0 = *reinterpret_cast<const float4 *>(As + (cc + 0) * LDA + j0);
             const float4 L1 = *reinterpret_cast<const float4 *>(As + (cc + 1) * LDA + j0);
@@ -110,14 +115,12 @@ __device__ __forceinline__ bool chol_solve(float *As, float *ys, float *dinv, co
             for (int q = 0; q < RPT; q++) {
                 if (q * NT + NT - 1 < cc) continue;  // this whole row group is above the tile (uniform)
                 const int i = tid + q * NT;
-                if (i >= cc) {
-                    float4 av = *reinterpret_cast<float4 *>(As + i * LDA + cc);
-                    av.x -= x[q][0] * L0.x + x[q][1] * L0.y + x[q][2] * L0.z + x[q][3] * L0.w;
-                    av.y -= x[q][0] * L1.x + x[q][1] * L1.y + x[q][2] * L1.z + x[q][3] * L1.w;
-                    av.z -= x[q][0] * L2.x + x[q][1] * L2.y + x[q][2] * L2.z + x[q][3] * L2.w;
-                    av.w -= x[q][0] * L3.x + x[q][1] * L3.y + x[q][2] * L3.z + x[q][3] * L3.w;
-                    *reinterpret_cast<float4 *>(As + i * LDA + cc) = av;
-                }
+                float4 av = *reinterpret_cast<float4 *>(As + i * LDA + cc);
+                av.x -= x[q][0] * L0.x + x[q][1] * L0.y + x[q][2] * L0.z + x[q][3] * L0.w;
+                av.y -= x[q][0] * L1.x + x[q][1] * L1.y + x[q][2] * L1.z + x[q][3] * L1.w;
+                av.z -= x[q][0] * L2.x + x[q][1] * L2.y + x[q][2] * L2.z + x[q][3] * L2.w;
+                av.w -= x[q][0] * L3.x + x[q][1] * L3.y + x[q][2] * L3.z + x[q][3] * L3.w;
+                *reinterpret_cast<float4 *>(As + i * LDA + cc) = av;
             }
         }
         cta_sync<NW>();

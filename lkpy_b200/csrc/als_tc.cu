@@ -157,6 +157,16 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                                 ? tmem_base + ((uint32_t)((warp & 1) * 16) << 16) + (uint32_t)((warp >> 1) * 64)
                                 : tmem_base + (uint32_t)(warp * 64);
 
+    // optional per-phase cycle accounting (thread 0's view, barrier waits included)
+    long long t_prev = clock64();
+    auto prof = [&](int idx) {
+        if (a.d_prof != nullptr && tid == 0) {
+            const long long t = clock64();
+            atomicAdd(a.d_prof + idx, (unsigned long long)(t - t_prev));
+            t_prev = t;
+        }
+    };
+
     uint32_t free_par = 0;  // bit s: parity of the number of commits issued on stage_free[s]
     uint32_t full_par = 0;  // bit c: parity of the number of commits seen on acc_full[c]
 
@@ -166,6 +176,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
         const int64_t g = s_misc[0];
         __syncthreads();
         if (g * WARPS >= a.n_chunks) break;
+        prof(0);
         const int64_t ci = g * WARPS + warp;
         const bool active = ci < a.n_chunks;
         int row = -1, begin = 0, len = 0, nparts = 1, slot0 = 0, part = 0, split_idx = 0;
@@ -297,6 +308,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             cp_async_wait<0>();
         }
         __syncthreads();  // every warp has issued its MMAs; chunk metadata is visible
+        prof(1);
 
         // ------------------------------------------------------------------
         // phase 2: drain the accumulators into the per-warp systems
@@ -315,6 +327,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             }
         }
         tmem_fence_after();
+        prof(2);
         const int n_loads = interleave ? 2 : 4;
         for (int p = 0; p < n_loads; p++) {
             if (interleave ? !(gram[2 * p] || gram[2 * p + 1]) : !gram[p]) continue;
@@ -374,8 +387,9 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                 __stcg(reinterpret_cast<float2 *>(slot) + lane, make_float2(y0, y1));
             }
         }
-        __threadfence();
+        if (parts[0] > 1 || parts[1] > 1 || parts[2] > 1 || parts[3] > 1) __threadfence();  // partial slots only
         __syncthreads();
+        prof(3);
 
         // split rows: the last part to arrive sums the slots in order
         bool solve = has_gram && nparts == 1;
@@ -406,6 +420,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             }
         }
         __syncwarp();
+        prof(4);
 
         // ------------------------------------------------------------------
         // phase 3: per-warp Cholesky solve and write-back
@@ -424,7 +439,9 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                 }
             }
         }
+        prof(5);
         __syncthreads();  // the systems alias the stage rings of the next group
+        prof(6);
     }
 
     tmem_fence_before();

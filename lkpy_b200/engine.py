@@ -19,6 +19,8 @@ from ._lib import LkAlsArgs, LkKnnBuildArgs, LkKnnGeom, LkKnnScoreArgs, check, l
 from .data import InteractionCSR
 
 DEFAULT_CHUNK_NNZ = 4096
+#: optional int64[8] device tensor receiving per-phase cycle counters of the ALS kernels (diagnostics)
+PROF_BUFFER = None
 
 
 @dataclass
@@ -198,6 +200,7 @@ def als_half_epoch(
     a.d_status = ptr(plan.status)
     a.vals_uniform = 1 if plan.vals_uniform else 0
     a.uniform_val = plan.uniform_val
+    a.d_prof = ptr(PROF_BUFFER)
     check(lib().lk_als_half_epoch(C.byref(a), stream_ptr()), "lk_als_half_epoch")
 
 
@@ -230,22 +233,33 @@ class KnnBuildPlan:
         g = LkKnnGeom()
         check(L.lk_knn_geometry(n_users, n_items, C.byref(g)), "lk_knn_geometry")
         tile_ptr = torch.empty(max(1, n_users * (g.n_subtiles + 1)), dtype=torch.int32, device=dev)
-        check(
-            L.lk_knn_tile_pointers(C.byref(g), ptr(ui.indptr), ptr(ui.indices), ptr(tile_ptr), stream_ptr()),
-            "lk_knn_tile_pointers",
-        )
         cost = torch.empty(n_items, dtype=torch.int64, device=dev)
-        check(
-            L.lk_knn_row_cost(C.byref(g), ptr(ui.indptr), ptr(iu.indptr), ptr(iu.indices), ptr(cost), stream_ptr()),
-            "lk_knn_row_cost",
-        )
-        order = torch.argsort(cost, descending=True, stable=True).to(torch.int32)
         tie = torch.empty(max(1, L.lk_knn_tie_scratch_ints(C.byref(g))), dtype=torch.int32, device=dev)
-        return cls(
-            ui, iu, g, tile_ptr, cost, order, tie,
+        plan = cls(
+            ui, iu, g, tile_ptr, cost, torch.empty(0, dtype=torch.int32, device=dev), tie,
             torch.zeros(1, dtype=torch.int32, device=dev),
             torch.zeros(1, dtype=torch.int32, device=dev),
         )  # fmt: skip
+        plan.prepare()
+        return plan
+
+    def prepare(self) -> None:
+        """(Re)compute tile pointers, row costs and the cost-ordered work list into the plan's buffers."""
+        L = lib()
+        g = self.geom
+        check(
+            L.lk_knn_tile_pointers(
+                C.byref(g), ptr(self.ui.indptr), ptr(self.ui.indices), ptr(self.tile_ptr), stream_ptr()
+            ),
+            "lk_knn_tile_pointers",
+        )
+        check(
+            L.lk_knn_row_cost(
+                C.byref(g), ptr(self.ui.indptr), ptr(self.iu.indptr), ptr(self.iu.indices), ptr(self.cost), stream_ptr()
+            ),
+            "lk_knn_row_cost",
+        )
+        self.order = torch.argsort(self.cost, descending=True, stable=True).to(torch.int32)
 
     def _args(self, order: torch.Tensor, min_sim: float, save_nbrs: int) -> LkKnnBuildArgs:
         a = LkKnnBuildArgs()
@@ -273,9 +287,16 @@ class KnnBuildPlan:
         dev = self.ui.indptr.device
         n_items, H, K = self.geom.n_items, self.geom.n_halves, int(save_nbrs)
         order = self.order if order is None else order.to(torch.int32).contiguous()
-        part_cols = torch.empty(n_items * H * K, dtype=torch.int32, device=dev)
-        part_vals = torch.empty(n_items * H * K, dtype=torch.float32, device=dev)
-        part_cnt = torch.zeros(n_items * H, dtype=torch.int32, device=dev)
+        ws = self.extra.get(("topk", K))
+        if ws is None:  # workspaces are allocated once per plan and K, reused by every build
+            ws = (
+                torch.empty(n_items * H * K, dtype=torch.int32, device=dev),
+                torch.empty(n_items * H * K, dtype=torch.float32, device=dev),
+                torch.empty(n_items * H, dtype=torch.int32, device=dev),
+            )
+            self.extra[("topk", K)] = ws
+        part_cols, part_vals, part_cnt = ws
+        part_cnt.zero_()
         self.status.zero_()
         a = self._args(order, min_sim, K)
         a.d_part_cols, a.d_part_vals, a.d_part_cnt = ptr(part_cols), ptr(part_vals), ptr(part_cnt)
@@ -287,7 +308,6 @@ class KnnBuildPlan:
             L.lk_knn_merge_topk(C.byref(a), ptr(out_cols), ptr(out_vals), ptr(out_cnt), stream_ptr()),
             "lk_knn_merge_topk",
         )
-        self.extra["keepalive"] = (part_cols, part_vals, part_cnt, order)
         return out_cols, out_vals, out_cnt
 
     def build_unbounded(
