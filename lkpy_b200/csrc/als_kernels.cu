@@ -434,7 +434,8 @@ __global__ void otor_reduce_kernel(const float *__restrict__ partial, int nblock
     out[e] = s;
 }
 
-int launch_als_tc(const lk_als_args &a, cudaStream_t st);  // als_tc.cu
+int launch_als_tc(const lk_als_args &a, cudaStream_t st);   // als_tc.cu  (tensor-core Gram, shared-memory solve)
+int launch_als_tcr(const lk_als_args &a, cudaStream_t st);  // als_tcr.cu (tensor-core Gram, register solve)
 
 static int pad_features(int k) { return k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : -1; }
 
@@ -575,8 +576,13 @@ int lk_als_half_epoch(const lk_als_args *args, void *stream)
         LK_CUDA_TRY(cudaMemsetAsync(a.d_split_counters, 0, sizeof(int32_t) * a.n_split_rows, st));
     if (a.other_dtype == LK_DTYPE_F32) return dispatch_k<float>(a, st);
     // k = 64, bf16 rows, unweighted / uniformly weighted Gram: tensor-core kernel (als_tc.cu)
-    const int rc = launch_als_tc(a, st);
-    if (rc <= 0) return rc;
+    // LK_ALS_TC selects the kernel for diagnostics: 0 = SIMT, 1 = first-generation tensor-core
+    // kernel, anything else / unset = the register-solve tensor-core kernel.
+    const char *sel = getenv("LK_ALS_TC");
+    if (!(sel && sel[0] == '0')) {
+        const int rc = (sel && sel[0] == '1') ? launch_als_tc(a, st) : launch_als_tcr(a, st);
+        if (rc <= 0) return rc;
+    }
     return dispatch_k<__nv_bfloat16>(a, st);
 }
 

@@ -34,7 +34,7 @@
 // Two M=64 accumulators share 64 TMEM columns (lanes 0-15 / 16-31 of every
 // quarter, the "interleaved" allocation), so a CTA needs 128 columns.
 
-#include "als_common.cuh"
+#include "tc_common.cuh"
 
 namespace lk {
 
@@ -54,65 +54,9 @@ constexpr int SLOTF = KP * KP + KP;
 constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + WARPS * WARP_BYTES + 2 * WARPS * KP * 4 +
                            (WARPS * NSTAGE + WARPS) * 8 + 16 + 64 * 4;
 
-// instruction descriptor: D=f32, A=B=bf16, both MN-major, N=64, M=64 (mma_sm100_desc.hpp InstrDescriptor)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) |
-                           ((64u >> 4) << 24);
-// shared-memory descriptor, high part: SBO = 1024 B between 8-row groups along K, version 1, SWIZZLE_128B
-constexpr uint64_t DESC_HI = (uint64_t(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-constexpr uint64_t DESC_LBO = uint64_t(1) << 16;  // single 64-wide MN atom: leading offset unused
+using tcd::DESC_HI;
+using tcd::DESC_LBO;
 }  // namespace tc
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ void umma_bf16_64x64x16(uint32_t tmem_d, uint64_t desc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %3, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %1, %2, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc), "r"(tc::IDESC), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// 32 lanes x 64 consecutive 32-bit columns
-__device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t (&r)[64])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
-          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
-          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
-          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // interleave != 0: two accumulators share 64 columns (TMEM lanes 0-15 / 16-31 of each
 // quarter), 128 columns per CTA; interleave == 0: one accumulator per 64 columns, 256 per CTA.
@@ -460,8 +404,6 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
     if (a.k != tc::KP || a.other_dtype != LK_DTYPE_BF16) return 1;
     if (a.mode == LK_ALS_IMPLICIT && !a.vals_uniform) return 1;
     if (reinterpret_cast<uintptr_t>(a.d_other) % 16 != 0) return 1;
-    if (const char *e = getenv("LK_ALS_TC"))
-        if (e[0] == '0') return 1;
     int interleave = 1;
     if (const char *e = getenv("LK_ALS_TC_INTERLEAVE")) interleave = e[0] != '0';
     const int cols = interleave ? tc::TMEM_COLS : 2 * tc::TMEM_COLS;

@@ -40,10 +40,11 @@ def _oracle(mode, csr, this, other, reg):
     return oracle.als_half_f64(mode, csr, this, other, otor_mat=o64, reg=reg, bf16_other=True)
 
 
-@pytest.mark.parametrize("interleave", ["1", "0"])
+# generation "2" = als_tcr.cu (register-resident solve, the default), "1" = als_tc.cu
+@pytest.mark.parametrize("gen,interleave", [("2", "1"), ("1", "1"), ("1", "0")])
 @pytest.mark.parametrize("mode", ["implicit", "explicit"])
-def test_tc_kernel_parity(cuda_lib, monkeypatch, mode, interleave):
-    monkeypatch.setenv("LK_ALS_TC", "1")
+def test_tc_kernel_parity(cuda_lib, monkeypatch, mode, gen, interleave):
+    monkeypatch.setenv("LK_ALS_TC", gen)
     monkeypatch.setenv("LK_ALS_TC_INTERLEAVE", interleave)
     inter = small_synth(900, 500, 40000, seed=21)
     rng = np.random.default_rng(21)
@@ -66,12 +67,13 @@ def test_tc_kernel_parity(cuda_lib, monkeypatch, mode, interleave):
         # the SIMT kernel on the same inputs agrees to rounding
         monkeypatch.setenv("LK_ALS_TC", "0")
         simt, _, _ = _run(mode, csr, this, other, 0.1)
-        monkeypatch.setenv("LK_ALS_TC", "1")
+        monkeypatch.setenv("LK_ALS_TC", gen)
         assert rel_fro(got, simt) < 2e-5
 
 
-def test_tc_split_rows_deterministic(cuda_lib, monkeypatch):
-    monkeypatch.setenv("LK_ALS_TC", "1")
+@pytest.mark.parametrize("gen", ["2", "1"])
+def test_tc_split_rows_deterministic(cuda_lib, monkeypatch, gen):
+    monkeypatch.setenv("LK_ALS_TC", gen)
     inter = small_synth(300, 200, 20000, seed=5)
     _ui, iu = data.als_implicit_matrices(inter, 40.0)
     rng = np.random.default_rng(5)
@@ -89,7 +91,7 @@ def test_tc_split_rows_deterministic(cuda_lib, monkeypatch):
 
 def test_tc_non_uniform_weights_fall_back(cuda_lib, monkeypatch):
     """use_ratings=True confidences are not uniform: the SIMT kernel must take the launch."""
-    monkeypatch.setenv("LK_ALS_TC", "1")
+    monkeypatch.setenv("LK_ALS_TC", "2")
     inter = small_synth(400, 300, 15000, seed=8)
     ui, _ = data.als_implicit_matrices(inter, 40.0, use_ratings=True)
     rng = np.random.default_rng(8)
