@@ -42,7 +42,8 @@ KNN_MIN_SIM = 1e-6
 
 
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(*a, file=sys.stderr, flush=True)
 
 
 # ---------------------------------------------------------------------------
@@ -350,9 +351,11 @@ def main() -> None:
             ms = float(t.item())
         s = 2 if tag == "bf16" else 4
         nnz = inter.nnz
-        alg = als_half_bytes(inter.n_users, inter.n_items, nnz, K, s, False) + als_half_bytes(
-            inter.n_items, inter.n_users, nnz, K, s, False
-        )
+        # per GPU: each rank gathers for its row shard only (1/world of the nonzeros and rows)
+        alg = (
+            als_half_bytes(inter.n_users, inter.n_items, nnz, K, s, False)
+            + als_half_bytes(inter.n_items, inter.n_users, nnz, K, s, False)
+        ) / world
         per_epoch_kernel_ms = float(np.sum(kern_ms)) / args.steps if kern_ms else float("nan")
         achieved = alg / (per_epoch_kernel_ms * 1e-3) / 1e9 if kern_ms else float("nan")
         results[tag] = {

@@ -576,11 +576,11 @@ int lk_als_half_epoch(const lk_als_args *args, void *stream)
         LK_CUDA_TRY(cudaMemsetAsync(a.d_split_counters, 0, sizeof(int32_t) * a.n_split_rows, st));
     if (a.other_dtype == LK_DTYPE_F32) return dispatch_k<float>(a, st);
     // k = 64, bf16 rows, unweighted / uniformly weighted Gram: tensor-core kernel (als_tc.cu)
-    // LK_ALS_TC selects the kernel for diagnostics: 0 = SIMT, 1 = first-generation tensor-core
-    // kernel, anything else / unset = the register-solve tensor-core kernel.
+    // LK_ALS_TC selects the kernel for diagnostics: 0 = SIMT, 2 = the register-solve variant
+    // (als_tcr.cu, measured slower in round 1), anything else / unset = als_tc.cu.
     const char *sel = getenv("LK_ALS_TC");
     if (!(sel && sel[0] == '0')) {
-        const int rc = (sel && sel[0] == '1') ? launch_als_tc(a, st) : launch_als_tcr(a, st);
+        const int rc = (sel && sel[0] == '2') ? launch_als_tcr(a, st) : launch_als_tc(a, st);
         if (rc <= 0) return rc;
     }
     return dispatch_k<__nv_bfloat16>(a, st);

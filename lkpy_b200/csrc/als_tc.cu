@@ -52,7 +52,16 @@ static_assert(WARP_BYTES >= NSTAGE * STAGE_BYTES && WARP_BYTES % 1024 == 0, "sta
 constexpr int TMEM_COLS = 128;
 constexpr int SLOTF = KP * KP + KP;
 constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + WARPS * WARP_BYTES + 2 * WARPS * KP * 4 +
-                           (WARPS * NSTAGE + WARPS) * 8 + 16 + 64 * 4;
+                           (WARPS * NSTAGE + WARPS) * 8 + 16 + 64 * 4 + 128 + 256 /* ones tile */;
+constexpr int TMEM_Y_COLS = 32;  // second allocation: 64x8 right-hand-side accumulators
+
+// y = M^T w on the tensor cores too (uniform weights: w = (v+1) * ones): D2[64x8] += tile^T . B[16x8]
+// with B a constant 16x8 bf16 tile whose first column is 1 (MN-major, no swizzle: two 8-row core
+// matrices of 128 B).  Instruction descriptor as IDESC with N = 8; B's shared-memory descriptor:
+// LBO = 128 B between the 8-row groups along K, SBO unused, version 1, SWIZZLE_NONE.
+constexpr uint32_t IDESC_Y = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((8u >> 3) << 17) |
+                             ((64u >> 4) << 24);
+constexpr uint64_t DESC_Y_HI = (uint64_t(128 >> 4) << 16) | (uint64_t(128 >> 4) << 32) | (1ull << 46);
 
 using tcd::DESC_HI;
 using tcd::DESC_LBO;
@@ -78,6 +87,10 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     uint64_t *acc_full = bars + WARPS * NSTAGE;   // [WARPS]
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(acc_full + WARPS);
     int *s_misc = reinterpret_cast<int *>(s_tmem + 4);  // [0] group, then per-chunk metadata [8 + 8*c ...]
+    unsigned char *ones_tile = reinterpret_cast<unsigned char *>(s_misc + 64);
+    ones_tile += (128u - (smem_u32(ones_tile) & 127u)) & 127u;
+    // the right-hand side goes through the tensor cores when the weights are uniform
+    const bool ymma = (MODE == LK_ALS_IMPLICIT) && interleave != 0;
 
     const __nv_bfloat16 *__restrict__ other = reinterpret_cast<const __nv_bfloat16 *>(a.d_other);
     constexpr int k = KP;
@@ -90,12 +103,26 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
                      "r"((uint32_t)(interleave ? TMEM_COLS : 2 * TMEM_COLS))
                      : "memory");
+        if (ymma)
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(s_tmem + 1)),
+                         "r"((uint32_t)TMEM_Y_COLS)
+                         : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (tid < 64) {
+        // ones tile: row r (16 B) = bf16 {1, 0, 0, 0, 0, 0, 0, 0}
+        reinterpret_cast<uint32_t *>(ones_tile)[tid] = (tid & 3) == 0 ? 0x00003f80u : 0u;
+    }
+    fence_proxy_async();
     tmem_fence_before();
     __syncthreads();
     tmem_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_y = ymma ? s_tmem[1] : 0u;
+    // rhs accumulator of warp w: 8 columns per pair, same lane interleave as the Gram
+    const uint32_t my_yacc = tmem_y + ((uint32_t)((warp & 1) * 16) << 16) + (uint32_t)((warp >> 1) * 8);
+    const uint64_t ydesc = DESC_Y_HI | (uint64_t)((smem_u32(ones_tile) >> 4) & 0x3fffu);
     // accumulator of warp w: columns 64*(w/2), lanes 16*(w%2) of every 32-lane quarter
     const uint32_t my_acc = interleave
                                 ? tmem_base + ((uint32_t)((warp & 1) * 16) << 16) + (uint32_t)((warp >> 1) * 64)
@@ -227,13 +254,15 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                                 const uint64_t desc =
                                     DESC_HI | DESC_LBO | (uint64_t)(((sbase + kk * 2048) >> 4) & 0x3fffu);
                                 umma_bf16_64x64x16(my_acc, desc, (it > 0 || kk > 0) ? 1u : 0u);
+                                if (ymma) umma_bf16_ab(my_yacc, desc, ydesc, IDESC_Y, (it > 0 || kk > 0) ? 1u : 0u);
                             }
                             umma_commit(&stage_free[s]);
                             if (it == n_it - 1) umma_commit(&acc_full[warp]);
                         }
                         free_par ^= (1u << s);
-                        // 4. right-hand side from the same tile: lane owns features 2*lane, 2*lane+1
-                        {
+                        // 4. right-hand side from the same tile on the SIMT side when it cannot go
+                        //    through the tensor cores: lane owns features 2*lane, 2*lane+1
+                        if (!ymma) {
                             const unsigned char *st = wreg + s * STAGE_BYTES;
                             const int chunk = lane >> 2, within = (lane & 3) * 4;
                             for (int r = 0; r < nrows; r++) {
@@ -320,9 +349,28 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                 }
             }
         }
+        if (ymma) {
+            // right-hand sides from their TMEM accumulators: y = (v + 1) * column sums
+            const float w1 = a.uniform_val + 1.0f;
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                if (!(gram[2 * p] || gram[2 * p + 1])) continue;
+                uint32_t ry[8];
+                tmem_ld_32x32b_x8(tmem_y + ((uint32_t)(32 * warp) << 16) + (uint32_t)(p * 8), ry);
+                const int c = 2 * p + (lane >> 4);
+                const int gi = 16 * warp + (lane & 15);
+                if (gram[c]) {
+                    const float yy = w1 * __uint_as_float(ry[0]);
+                    if (parts[c] == 1)
+                        ys_all[c * KP + gi] = yy;
+                    else
+                        __stcg(a.d_partials + (size_t)slotc[c] * SLOTF + KP * KP + gi, yy);
+                }
+            }
+        }
         tmem_fence_before();
-        // right-hand side of this warp's chunk
-        if (has_gram) {
+        // right-hand side of this warp's chunk (SIMT path)
+        if (has_gram && !ymma) {
             if (nparts == 1) {
                 ys[2 * lane] = y0;
                 ys[2 * lane + 1] = y1;
@@ -391,6 +439,10 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     tmem_fence_before();
     __syncthreads();
     if (warp == 0) {
+        if (ymma)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_y),
+                         "r"((uint32_t)tc::TMEM_Y_COLS)
+                         : "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)(interleave ? tc::TMEM_COLS : 2 * tc::TMEM_COLS))
                      : "memory");
@@ -415,13 +467,13 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
     if (a.mode == LK_ALS_IMPLICIT) {
         auto kern = als_tc_kernel<LK_ALS_IMPLICIT>;
         LK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        occ = std::max(1, std::min(occ, 512 / cols));
+        occ = std::max(1, std::min(occ, 512 / (cols + tc::TMEM_Y_COLS)));
         const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
         kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave);
     } else {
         auto kern = als_tc_kernel<LK_ALS_EXPLICIT>;
         LK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        occ = std::max(1, std::min(occ, 512 / cols));
+        occ = std::max(1, std::min(occ, 512 / (cols + tc::TMEM_Y_COLS)));
         const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
         kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave);
     }
