@@ -141,9 +141,10 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     uint32_t free_par = 0;  // bit s: parity of the number of commits issued on stage_free[s]
     uint32_t full_par = 0;  // bit c: parity of the number of commits seen on acc_full[c]
 
+    // the index of the next group is fetched one group ahead (during the solve phase)
+    if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);
+    __syncthreads();
     for (;;) {
-        if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);
-        __syncthreads();
         const int64_t g = s_misc[0];
         __syncthreads();
         if (g * WARPS >= a.n_chunks) break;
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
         // ------------------------------------------------------------------
         // phase 3: per-warp Cholesky solve and write-back
         // ------------------------------------------------------------------
+        if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);  // next group, read after the closing barrier
         if (active) {
             float *thisrow = a.d_this + (size_t)row * k;
             if (solve) {
@@ -464,6 +466,7 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
     // 3 CTAs per SM by shared memory (73 KB) and registers; TMEM allows 512 / cols.  (The occupancy
     // API returned 1 for the user-half launch on the B200 box, so the design figure is used.)
     int occ = 3;
+    if (const char *e = getenv("LK_ALS_TC_OCC")) occ = std::max(1, std::min(3, atoi(e)));  // diagnostics
     if (a.mode == LK_ALS_IMPLICIT) {
         auto kern = als_tc_kernel<LK_ALS_IMPLICIT>;
         LK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
