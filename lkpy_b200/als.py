@@ -160,7 +160,7 @@ class ALSTrainerBase(ModelTrainer):
         raise NotImplementedError
 
     # -- epoch ---------------------------------------------------------------
-    def _half(self, plan, this, other, other_bf16, reg: float) -> torch.Tensor:
+    def _half(self, plan, this, other, other_bf16, reg: float, replicas=None, replica_row0: int = 0) -> torch.Tensor:
         plan.sqdelta.zero_()
         otor = None
         gather = other
@@ -174,7 +174,9 @@ class ALSTrainerBase(ModelTrainer):
         if self.kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        engine.als_half_epoch(plan, self.MODE, this, gather, otor=otor, reg=reg)
+        engine.als_half_epoch(
+            plan, self.MODE, this, gather, otor=otor, reg=reg, replicas=replicas, replica_row0=replica_row0
+        )
         if self.kernel_events is not None:
             e1.record()
             self.kernel_events.append((e0, e1))

@@ -22,6 +22,8 @@ on CPU tensors in ``tests/test_parallel.py``).
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -108,24 +110,64 @@ class ShardedImplicitMFTrainer(ImplicitMFTrainer):
         # every rank must start from the same factors (rank 0's draw)
         dist.broadcast(self.d_users, 0, group=group)
         dist.broadcast(self.d_items, 0, group=group)
+        self.user_peers = self.item_peers = None
+        if os.environ.get("LK_ALS_PEER_WRITES", "1") != "0":
+            self._try_peer_tables()
         torch.cuda.empty_cache()
+
+    def _try_peer_tables(self) -> None:
+        """
+        Fused exchange: put both factor tables in symmetric (peer-mapped) memory so that the solve
+        kernel's epilogue stores every new row straight into all replicas over NVLink
+        (``lk_als_args.d_replicas``) — the all-gather disappears into the kernel.  Falls back to
+        the padded NCCL all-gather when symmetric memory is unavailable.
+        """
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            grp = self.group if self.group is not None else dist.group.WORLD
+            tabs, peers = [], []
+            for t in (self.d_users, self.d_items):
+                st = symm_mem.empty(tuple(t.shape), dtype=t.dtype, device=t.device)
+                st.copy_(t)
+                hdl = symm_mem.rendezvous(st, grp)
+                off = st.data_ptr() - int(hdl.buffer_ptrs[self.rank])
+                peers.append([int(hdl.buffer_ptrs[r]) + off for r in range(self.world) if r != self.rank])
+                tabs.append((st, hdl))
+            (self.d_users, self._hu), (self.d_items, self._hq) = tabs
+            self.user_peers, self.item_peers = peers
+        except Exception as e:  # noqa: BLE001
+            self.user_peers = self.item_peers = None
+            if self.rank == 0:
+                print(f"[lkpy_b200] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
 
     def train_epoch_device(self):
         self.u_plan.status.zero_()
         self.i_plan.status.zero_()
         ulo, uhi = self.u_slice
         ilo, ihi = self.i_slice
-        du = self._half(self.u_plan, self.d_users[ulo:uhi], self.d_items, self.d_items_bf16, self.config.user_reg)
-        allgather_rows(self.d_users, self.u_bounds, self.rank, self.world, self.group)
-        di = self._half(self.i_plan, self.d_items[ilo:ihi], self.d_users, self.d_users_bf16, self.config.item_reg)
-        allgather_rows(self.d_items, self.i_bounds, self.rank, self.world, self.group)
+        if self.user_peers is not None:
+            # peer-write path: rows land in every replica from inside the kernel; the all-reduce of
+            # the Σ‖Δ‖² scalar is the only collective and doubles as the "all shards written" barrier
+            du = self._half(self.u_plan, self.d_users[ulo:uhi], self.d_items, self.d_items_bf16,
+                            self.config.user_reg, replicas=self.user_peers, replica_row0=ulo)  # fmt: skip
+            dist.all_reduce(du, group=self.group)
+            di = self._half(self.i_plan, self.d_items[ilo:ihi], self.d_users, self.d_users_bf16,
+                            self.config.item_reg, replicas=self.item_peers, replica_row0=ilo)  # fmt: skip
+            dist.all_reduce(di, group=self.group)
+        else:
+            du = self._half(self.u_plan, self.d_users[ulo:uhi], self.d_items, self.d_items_bf16, self.config.user_reg)
+            allgather_rows(self.d_users, self.u_bounds, self.rank, self.world, self.group)
+            di = self._half(self.i_plan, self.d_items[ilo:ihi], self.d_users, self.d_users_bf16, self.config.item_reg)
+            allgather_rows(self.d_items, self.i_bounds, self.rank, self.world, self.group)
         self.epochs_trained += 1
         return du, di
 
     def train_epoch(self):
         du, di = self.train_epoch_device()
         d = torch.cat([du, di])
-        dist.all_reduce(d, group=self.group)  # Σ‖Δ‖² over the shards
+        if self.user_peers is None:
+            dist.all_reduce(d, group=self.group)  # Σ‖Δ‖² over the shards
         st = torch.stack([self.u_plan.status, self.i_plan.status]).flatten().clone()
         dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
         self._sync_host()
@@ -140,9 +182,11 @@ def sharded_knn_build_topk(
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Item-sharded truncated build; every rank returns the full fixed-width result."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    cost = plan.cost.cpu().numpy()
-    mine = deal_by_cost(cost, world)[rank]
-    order = torch.from_numpy(np.ascontiguousarray(mine.astype(np.int32))).to(plan.cost.device)
+    # deal_by_cost on the device (no host sync): plan.order is already most-expensive-first
+    pos = torch.arange(plan.order.numel(), device=plan.order.device)
+    lap, off = pos // world, pos % world
+    owner = torch.where(lap % 2 == 0, off, world - 1 - off)
+    order = plan.order[owner == rank].contiguous()
     cols, vals, cnt = plan.build_topk(min_sim, save_nbrs, order)
     # rows are disjoint across ranks: zero the padding, then a sum is a gather
     K = cols.shape[1]
