@@ -80,9 +80,15 @@ class ClockSampler:
     def _read(self):
         assert self.proc and self.proc.stdout
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def wait_first(self, timeout: float = 8.0) -> None:
+        """nvidia-smi takes a few hundred ms to print its first row: block until it is sampling."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin: float | None = None, t_end: float | None = None) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -90,9 +96,20 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        rows = list(self.rows)
+        window = "timed region"
+        if t_begin is not None and t_end is not None:
+            inside = [r for t, r in rows if t_begin <= t <= t_end + 0.02]
+            if len(inside) >= 2:
+                sel = inside
+            else:  # region shorter than two sampling periods: use the samples under the same load around it
+                sel = [r for t, r in rows if t_begin - 0.5 <= t <= t_end + 0.1]
+                window = "timed region +/- warm-up epochs (region shorter than two 20 ms samples)"
+        else:
+            sel = [r for _, r in rows]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in sel:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -105,6 +122,7 @@ class ClockSampler:
             "sm_mhz": float(np.median(sm)) if sm else None,
             "sm_max_mhz": float(max(mx)) if mx else None,
             "samples": len(sm),
+            "window": window,
             "reasons": sorted(reasons),
         }
 
@@ -132,6 +150,14 @@ def load_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(key: str, world: int) -> float | None:
+    """DRAM bytes per launch from the committed ncu --set full capture (N=1, default workload only)."""
+    f = ROOT / "profiles" / "r01_traffic.json"
+    if world != 1 or not f.exists():
+        return None
+    return float(json.loads(f.read_text()).get(key, 0)) or None
+
+
 # ---------------------------------------------------------------------------
 # CPU baseline (oracle port of src/accel; the Rust crate cannot be built here)
 # ---------------------------------------------------------------------------
@@ -148,8 +174,10 @@ def _slice_rows(csr, lo: int, hi: int):
 
 def cpu_als_epoch_estimate(ui, iu, p, q, budget_s: float, threads: int) -> dict:
     """
-    Time the oracle (BLAS sgemm Gram + LAPACK sposv, all host threads) on leading
-    row ranges of both halves and scale by nnz to a full epoch.
+    Time the oracle (BLAS sgemm Gram + LAPACK sposv) on leading row ranges of both halves and
+    scale by nnz to a full epoch.  The thread count is the fastest of {all host threads the BLAS
+    allows, 32, 16, 8 (the reference's default, schemas/settings.py:183)} on a calibration slice:
+    on many-core hosts the row-parallel loop stops scaling well before all cores are busy.
     """
     import oracle
 
@@ -158,29 +186,37 @@ def cpu_als_epoch_estimate(ui, iu, p, q, budget_s: float, threads: int) -> dict:
         out = {}
         total = 0.0
         parts = []
+        top = oracle.blas_threads(threads)
+        cands = sorted({t for t in (top, 32, 16, 8) if t <= top}, reverse=True)
+        used = []
         for name, csr, this, other in (("user", ui, p, q), ("item", iu, q, p)):
-            o32, _ = oracle.otor(other[: min(len(other), 2000)], REG)  # content irrelevant for timing
             o32 = (other.T @ other + np.eye(K, dtype=np.float32) * REG).astype(np.float32)
-            # calibrate on ~1% of the nonzeros, then size the sample to the budget
+            # calibrate on ~3% of the nonzeros (thread count + rate), then size the sample to the budget
             nnz = csr.nnz
-            rows_cal = int(np.searchsorted(csr.indptr, nnz // 100))
-            rows_cal = max(rows_cal, 16)
-            t0 = time.perf_counter()
-            oracle.als_half("implicit", _slice_rows(csr, 0, rows_cal), this[:rows_cal], other, otor_mat=o32, threads=threads)
-            t_cal = time.perf_counter() - t0
+            rows_cal = max(int(np.searchsorted(csr.indptr, nnz // 32)), 16)
+            cal = _slice_rows(csr, 0, rows_cal)
+            best_t, t_cal = cands[0], float("inf")
+            for th in cands:
+                t0 = time.perf_counter()
+                oracle.als_half("implicit", cal, this[:rows_cal], other, otor_mat=o32, threads=th)
+                dt = time.perf_counter() - t0
+                if dt < t_cal:
+                    best_t, t_cal = th, dt
+            used.append(best_t)
             nnz_cal = int(csr.indptr[rows_cal])
             want_nnz = int(min(nnz, nnz_cal * (budget_s / 2) / max(t_cal, 1e-6)))
             rows = int(np.searchsorted(csr.indptr, want_nnz))
             rows = min(max(rows, rows_cal), csr.shape[0])
             t0 = time.perf_counter()
-            oracle.als_half("implicit", _slice_rows(csr, 0, rows), this[:rows], other, otor_mat=o32, threads=threads)
+            oracle.als_half("implicit", _slice_rows(csr, 0, rows), this[:rows], other, otor_mat=o32, threads=best_t)
             t = time.perf_counter() - t0
             nnz_s = int(csr.indptr[rows])
             est = t * nnz / max(nnz_s, 1)
-            parts.append(f"{name} half: {rows} rows / {nnz_s} nnz in {t:.2f}s")
+            parts.append(f"{name} half: {rows} rows / {nnz_s} nnz in {t:.2f}s on {best_t} threads")
             total += est
         out["epoch_ms"] = total * 1e3
-        out["sample"] = "; ".join(parts) + "; scaled by nnz to the full epoch"
+        out["threads"] = max(used)
+        out["sample"] = "; ".join(parts) + f"; scaled by nnz to the full epoch; thread counts tried {cands}"
         return out
     finally:
         oracle.use_scipy_blas(False)
@@ -242,6 +278,7 @@ def run_reference(args, rank: int) -> None:
     sample = ""
     for s in range(args.warmup + args.steps):
         r = cpu_als_epoch_estimate(ui, iu, p, q, per_step, threads)
+        threads = r["threads"]
         if s >= args.warmup:
             vals.append(r["epoch_ms"])
         sample = r["sample"]
@@ -327,18 +364,24 @@ def main() -> None:
         for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
             tr.train_epoch_device()
         barrier()
-        tr.kernel_events = []
         sampler = ClockSampler(local_rank)
         if rank == 0 and tag == "bf16":
             sampler.start()
+            sampler.wait_first()
+        if tag == "bf16":
+            for _ in range(3):  # every rank: the GPU stays under the same load while the sampler spins up
+                tr.train_epoch_device()
+        tr.kernel_events = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_begin = time.time()
         e0.record()
         for _ in range(args.steps):
             tr.train_epoch_device()
         e1.record()
         barrier()
-        clocks = sampler.stop() if (rank == 0 and tag == "bf16") else None
+        t_end = time.time()
+        clocks = sampler.stop(t_begin, t_end) if (rank == 0 and tag == "bf16") else None
         ms = e0.elapsed_time(e1) / args.steps
         kern_ms = [a.elapsed_time(b) for a, b in tr.kernel_events]
         tr.kernel_events = None
@@ -362,9 +405,11 @@ def main() -> None:
             "ms_per_epoch": ms,
             "solve_kernel_ms_per_epoch": per_epoch_kernel_ms,
             "roofline": {
-                "bound": "hbm", "kernel": "als_half_kernel (user + item launch of one epoch)",
+                "bound": "hbm",
+                "kernel": ("als_tc_kernel" if tag == "bf16" else "als_half_kernel") + " (user + item launch of one epoch)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes": alg, "peak_source": peak_src,
+                "traffic": ncu_traffic("als_tc_kernel_epoch_bytes", world) if tag == "bf16" else None,
+                "algorithmic_bytes": alg, "peak_source": peak_src,
             },
             "clocks": clocks,
         }  # fmt: skip
@@ -411,8 +456,8 @@ def main() -> None:
         p = (rng.standard_normal((inter.n_users, K)) * 0.1).astype(np.float32)
         q = (rng.standard_normal((inter.n_items, K)) * 0.1).astype(np.float32)
         r = cpu_als_epoch_estimate(ui, iu, p, q, args.cpu_seconds, threads)
-        cpu = {"value": r["epoch_ms"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]}
-        log(f"[bench] CPU baseline ({threads} threads): {r['epoch_ms']:.0f} ms/epoch  [{r['sample']}]")
+        cpu = {"value": r["epoch_ms"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+        log(f"[bench] CPU baseline ({r['threads']} threads): {r['epoch_ms']:.0f} ms/epoch  [{r['sample']}]")
         if knn is not None:
             kc = cpu_knn_estimate(knn.pop("_kui"), knn.pop("_kiu"), knn.pop("_cost"), args.cpu_seconds, threads)
             knn["cpu_baseline"] = {"value": kc["build_items_per_s"], "unit": "items/s", "cores": threads,
@@ -556,7 +601,8 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int = 0, world: int = 1) -
         "geometry": {"warps": plan.geom.warps, "tile_cols": plan.geom.tile_cols, "halves": plan.geom.n_halves,
                      "ctas_per_sm": plan.geom.ctas_per_sm},
         "roofline": {"bound": "hbm", "kernel": "knn_build_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes": alg,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("knn_build_kernel_bytes", world), "algorithmic_bytes": alg,
                      "peak_source": peak_src},
         "_kui": kui, "_kiu": kiu, "_cost": cost,
     }  # fmt: skip

@@ -111,11 +111,54 @@ def use_scipy_blas(enable: bool = True) -> None:
         except Exception:  # noqa: BLE001
             pass
 
+        global _blas_thread_cap
+        _blas_thread_cap = _openblas_caller_cap()
         lib().lk_oracle_set_blas(
             _capsule_ptr(cython_lapack, "sposv"), _capsule_ptr(cython_blas, "sgemm")
         )
     else:
+        _blas_thread_cap = 0
         lib().lk_oracle_set_blas(None, None)
+
+
+_blas_thread_cap = 0
+
+
+def _openblas_caller_cap() -> int:
+    """
+    SciPy's OpenBLAS keeps a fixed table of 2*MAX_THREADS work buffers shared by its own server
+    threads (one each) and every thread that calls into it; overflowing the table is a known crash
+    ("Bad memory unallocation").  Keep the number of OpenMP threads that call sgemm/sposv
+    concurrently safely below that: MAX_THREADS - 16 (48 for the MAX_THREADS=64 wheels).
+    """
+    cap = 48
+    try:
+        import re
+
+        import threadpoolctl
+
+        for info in threadpoolctl.threadpool_info():
+            if info.get("internal_api") != "openblas" or "scipy.libs" not in info.get("filepath", ""):
+                continue
+            L = C.CDLL(info["filepath"])
+            for name in ("scipy_openblas_get_config", "scipy_openblas_get_config64_", "openblas_get_config"):
+                f = getattr(L, name, None)
+                if f is None:
+                    continue
+                f.restype = C.c_char_p
+                m = re.search(rb"MAX_THREADS=(\d+)", f() or b"")
+                if m:
+                    cap = max(1, int(m.group(1)) - 16)
+                break
+    except Exception:  # noqa: BLE001
+        pass
+    return cap
+
+
+def blas_threads(threads: int = 0) -> int:
+    """The thread count ``als_half`` really uses for ``threads`` while the BLAS path is enabled."""
+    t = threads if threads > 0 else max_threads()
+    return min(t, _blas_thread_cap) if _blas_thread_cap else t
 
 
 def max_threads() -> int:
@@ -186,6 +229,8 @@ def als_half(
         otor_mat = np.ascontiguousarray(otor_mat, dtype=np.float32)
         op = otor_mat.ctypes.data_as(C.c_void_p)
     sq = C.c_double(0.0)
+    if _blas_thread_cap and not bf16_other:
+        threads = blas_threads(threads)
     fail = lib().lk_oracle_als_half_f32(
         m, indptr, cols, vals, n_rows, k, this, other, op, reg, int(bf16_other), threads, C.byref(sq)
     )
