@@ -187,21 +187,22 @@ def cpu_als_epoch_estimate(ui, iu, p, q, budget_s: float, threads: int) -> dict:
         total = 0.0
         parts = []
         top = oracle.blas_threads(threads)
-        cands = sorted({t for t in (top, 32, 16, 8) if t <= top}, reverse=True)
+        cands = sorted({t for t in (top, 32, 16, 8, 4) if t <= top}, reverse=True)
         used = []
         for name, csr, this, other in (("user", ui, p, q), ("item", iu, q, p)):
             o32 = (other.T @ other + np.eye(K, dtype=np.float32) * REG).astype(np.float32)
             # calibrate on ~3% of the nonzeros (thread count + rate), then size the sample to the budget
             nnz = csr.nnz
-            rows_cal = max(int(np.searchsorted(csr.indptr, nnz // 32)), 16)
+            rows_cal = max(int(np.searchsorted(csr.indptr, nnz // 20)), 16)
             cal = _slice_rows(csr, 0, rows_cal)
             best_t, t_cal = cands[0], float("inf")
             for th in cands:
-                t0 = time.perf_counter()
-                oracle.als_half("implicit", cal, this[:rows_cal], other, otor_mat=o32, threads=th)
-                dt = time.perf_counter() - t0
-                if dt < t_cal:
-                    best_t, t_cal = th, dt
+                for _rep in range(2):  # best of two: the first call at a new thread count pays the pool start-up
+                    t0 = time.perf_counter()
+                    oracle.als_half("implicit", cal, this[:rows_cal], other, otor_mat=o32, threads=th)
+                    dt = time.perf_counter() - t0
+                    if dt < t_cal:
+                        best_t, t_cal = th, dt
             used.append(best_t)
             nnz_cal = int(csr.indptr[rows_cal])
             want_nnz = int(min(nnz, nnz_cal * (budget_s / 2) / max(t_cal, 1e-6)))

@@ -34,7 +34,7 @@
 // Two M=64 accumulators share 64 TMEM columns (lanes 0-15 / 16-31 of every
 // quarter, the "interleaved" allocation), so a CTA needs 128 columns.
 
-#include "tc_common.cuh"
+#include "chol_tc.cuh"
 
 namespace lk {
 
@@ -52,7 +52,8 @@ static_assert(WARP_BYTES >= NSTAGE * STAGE_BYTES && WARP_BYTES % 1024 == 0, "sta
 constexpr int TMEM_COLS = 128;
 constexpr int SLOTF = KP * KP + KP;
 constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + WARPS * WARP_BYTES + 2 * WARPS * KP * 4 +
-                           (WARPS * NSTAGE + WARPS) * 8 + 16 + 64 * 4 + 128 + 256 /* ones tile */;
+                           (WARPS * NSTAGE + WARPS + 1) * 8 + 16 + 64 * 4 + 128 + 256 /* ones tile */;
+static_assert(ctc::WS_BYTES <= WARPS * WARP_BYTES, "the tensor-core solve workspace aliases the stage rings");
 constexpr int TMEM_Y_COLS = 32;  // second allocation: 64x8 right-hand-side accumulators
 
 // y = M^T w on the tensor cores too (uniform weights: w = (v+1) * ones): D2[64x8] += tile^T . B[16x8]
@@ -69,7 +70,10 @@ using tcd::DESC_LBO;
 
 // interleave != 0: two accumulators share 64 columns (TMEM lanes 0-15 / 16-31 of each
 // quarter), 128 columns per CTA; interleave == 0: one accumulator per 64 columns, 256 per CTA.
-template <int MODE>
+// TCS: the systems stay in TMEM and are solved by the blocked tensor-core Cholesky (chol_tc.cuh,
+// requires the interleaved allocation); otherwise they are drained to shared memory and solved
+// by one warp each (als_common.cuh).
+template <int MODE, bool TCS>
 __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const int interleave)
 {
     using namespace tc;
@@ -85,7 +89,8 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     uint64_t *bars = reinterpret_cast<uint64_t *>(ys_all + 2 * WARPS * KP);
     uint64_t *stage_free = bars + warp * NSTAGE;  // [NSTAGE] of this warp
     uint64_t *acc_full = bars + WARPS * NSTAGE;   // [WARPS]
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(acc_full + WARPS);
+    uint64_t *solve_bar = acc_full + WARPS;       // trailing-update MMAs of the tensor-core solve
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(solve_bar + 1);
     int *s_misc = reinterpret_cast<int *>(s_tmem + 4);  // [0] group, then per-chunk metadata [8 + 8*c ...]
     unsigned char *ones_tile = reinterpret_cast<unsigned char *>(s_misc + 64);
     ones_tile += (128u - (smem_u32(ones_tile) & 127u)) & 127u;
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     constexpr int k = KP;
 
     if (tid == 0) {
-        for (int i = 0; i < WARPS * NSTAGE + WARPS; i++) mbar_init(&bars[i], 1);
+        for (int i = 0; i < WARPS * NSTAGE + WARPS + 1; i++) mbar_init(&bars[i], 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
 
     uint32_t free_par = 0;  // bit s: parity of the number of commits issued on stage_free[s]
     uint32_t full_par = 0;  // bit c: parity of the number of commits seen on acc_full[c]
+    uint32_t solve_par = 0;
 
     // the index of the next group is fetched one group ahead (during the solve phase)
     if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);
@@ -167,6 +173,8 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             m[1] = nparts;
             m[2] = slot0 + part;
             m[3] = n_row;
+            m[4] = slot0;
+            m[5] = row;
         }
 
         // ------------------------------------------------------------------
@@ -302,6 +310,199 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
         }
         tmem_fence_after();
         prof(2);
+        if constexpr (TCS) {
+            // ------------------------------------------------------------------
+            // phase 2': finish the systems in place in TMEM (A = v*G + OtOr, or G + reg*n*I)
+            // ------------------------------------------------------------------
+            const ctc::Workspace ws = ctc::carve(base);  // aliases the stage rings: all their MMAs have completed
+            const int r16 = lane & 15, hh = lane >> 4;
+            const int gi = 16 * warp + r16;  // Gram row / feature held by this lane (of system 2p + hh)
+            const uint32_t lane_taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+            const bool anysplit = parts[0] > 1 || parts[1] > 1 || parts[2] > 1 || parts[3] > 1;
+            float *dsum = reinterpret_cast<float *>(s_misc + 44);  // [warp][system] partial |delta|^2
+            float yv[2] = {0.0f, 0.0f};
+            if (tid < 4) ws.bad[tid] = 0;
+            if (has_gram && !ymma) {  // SIMT right-hand side of this warp's chunk
+                if (nparts == 1) {
+                    ys[2 * lane] = y0;
+                    ys[2 * lane + 1] = y1;
+                } else {
+                    float *slot = a.d_partials + (size_t)(slot0 + part) * SLOTF + KP * KP;
+                    __stcg(reinterpret_cast<float2 *>(slot) + lane, make_float2(y0, y1));
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                if (!(gram[2 * p] || gram[2 * p + 1])) continue;
+                const int c = 2 * p + hh;
+                uint32_t r[64];
+                tmem_ld_32x32b_x64(lane_taddr + (uint32_t)(p * 64), r);
+                if (gram[c]) {
+                    if (parts[c] == 1) {
+                        if constexpr (MODE == LK_ALS_IMPLICIT) {
+                            const float v = a.uniform_val;
+                            const float4 *ot = reinterpret_cast<const float4 *>(a.d_otor + gi * k);
+#pragma unroll
+                            for (int q = 0; q < 16; q++) {
+                                const float4 o = __ldg(ot + q);
+                                r[4 * q + 0] = __float_as_uint(fmaf(v, __uint_as_float(r[4 * q + 0]), o.x));
+                                r[4 * q + 1] = __float_as_uint(fmaf(v, __uint_as_float(r[4 * q + 1]), o.y));
+                                r[4 * q + 2] = __float_as_uint(fmaf(v, __uint_as_float(r[4 * q + 2]), o.z));
+                                r[4 * q + 3] = __float_as_uint(fmaf(v, __uint_as_float(r[4 * q + 3]), o.w));
+                            }
+                        } else {
+                            const float regn = a.reg * (float)nrowc[c];
+#pragma unroll
+                            for (int i = 0; i < 64; i++)
+                                if (i == gi) r[i] = __float_as_uint(__uint_as_float(r[i]) + regn);
+                        }
+                    } else {
+                        float *slot = a.d_partials + (size_t)slotc[c] * SLOTF + gi * KP;
+#pragma unroll
+                        for (int q = 0; q < 16; q++)
+                            __stcg(reinterpret_cast<float4 *>(slot) + q,
+                                   make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+                    }
+                }
+                if ((gram[2 * p] && parts[2 * p] == 1) || (gram[2 * p + 1] && parts[2 * p + 1] == 1))
+                    ctc::tmem_st64(lane_taddr + (uint32_t)(p * 64), r);
+            }
+            if (ymma) {
+                const float w1 = a.uniform_val + 1.0f;
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    if (!(gram[2 * p] || gram[2 * p + 1])) continue;
+                    uint32_t ry[8];
+                    tmem_ld_32x32b_x8(tmem_y + ((uint32_t)(32 * warp) << 16) + (uint32_t)(p * 8), ry);
+                    const int c = 2 * p + hh;
+                    if (gram[c]) {
+                        const float yy = w1 * __uint_as_float(ry[0]);
+                        if (parts[c] == 1)
+                            yv[p] = yy;
+                        else
+                            __stcg(a.d_partials + (size_t)slotc[c] * SLOTF + KP * KP + gi, yy);
+                    }
+                }
+            }
+            tmem_fence_before();
+            if (anysplit) __threadfence();  // partial slots only
+            __syncthreads();
+            tmem_fence_after();
+            prof(3);
+            uint32_t solve_mask = 0;
+#pragma unroll
+            for (int c = 0; c < WARPS; c++)
+                if (gram[c] && parts[c] == 1) solve_mask |= 1u << c;
+            if (!ymma) {
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const int c = 2 * p + hh;
+                    if (gram[c] && parts[c] == 1) yv[p] = ys_all[c * KP + gi];
+                }
+            }
+            // split rows: the last part to arrive sums the slots in order, straight into TMEM
+            if (anysplit) {
+                if (lane == 0)
+                    s_misc[40 + warp] =
+                        (active && nparts > 1 && atomicAdd(a.d_split_counters + split_idx, 1) == nparts - 1) ? 1 : 0;
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < WARPS; c++) {
+                    if (!(parts[c] > 1 && s_misc[40 + c])) continue;
+                    __threadfence();
+                    const int p = c >> 1;
+                    const int slot0c = s_misc[8 + 8 * c + 4];
+                    uint32_t r[64];
+                    tmem_ld_32x32b_x64(lane_taddr + (uint32_t)(p * 64), r);
+                    if (hh == (c & 1)) {
+                        const float regn = a.reg * (float)nrowc[c];
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int pp = 0; pp < parts[c]; pp++) {
+                                const float4 t = __ldcg(
+                                    reinterpret_cast<const float4 *>(a.d_partials + (size_t)(slot0c + pp) * SLOTF + gi * KP) +
+                                    q);
+                                sacc.x += t.x, sacc.y += t.y, sacc.z += t.z, sacc.w += t.w;
+                            }
+                            if constexpr (MODE == LK_ALS_IMPLICIT) {
+                                const float4 o = __ldg(reinterpret_cast<const float4 *>(a.d_otor + gi * k) + q);
+                                const float v = a.uniform_val;
+                                sacc.x = fmaf(v, sacc.x, o.x), sacc.y = fmaf(v, sacc.y, o.y);
+                                sacc.z = fmaf(v, sacc.z, o.z), sacc.w = fmaf(v, sacc.w, o.w);
+                            } else {
+                                if (4 * q + 0 == gi) sacc.x += regn;
+                                if (4 * q + 1 == gi) sacc.y += regn;
+                                if (4 * q + 2 == gi) sacc.z += regn;
+                                if (4 * q + 3 == gi) sacc.w += regn;
+                            }
+                            r[4 * q + 0] = __float_as_uint(sacc.x), r[4 * q + 1] = __float_as_uint(sacc.y);
+                            r[4 * q + 2] = __float_as_uint(sacc.z), r[4 * q + 3] = __float_as_uint(sacc.w);
+                        }
+                        float sy = 0.0f;
+                        for (int pp = 0; pp < parts[c]; pp++)
+                            sy += __ldcg(a.d_partials + (size_t)(slot0c + pp) * SLOTF + KP * KP + gi);
+                        yv[p] = sy;
+                    }
+                    ctc::tmem_st64(lane_taddr + (uint32_t)(p * 64), r);
+                    solve_mask |= 1u << c;
+                }
+            }
+            prof(4);
+
+            // ------------------------------------------------------------------
+            // phase 3': blocked Cholesky on the tensor cores, write-back
+            // ------------------------------------------------------------------
+            if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);  // next group, read after the closing barrier
+            if (solve_mask) {
+                ctc::solve4(tmem_base, yv, ws, solve_bar, solve_par, tid);
+                __syncthreads();  // pivot flags
+                float dpart[2] = {0.0f, 0.0f};
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const int c = 2 * p + hh;
+                    if ((solve_mask >> c) & 1u) {
+                        const int rowc = s_misc[8 + 8 * c + 5];
+                        if (ws.bad[c]) {
+                            if (warp == 0 && r16 == 0) atomicCAS(a.d_status, 0, rowc + 1);
+                        } else {
+                            float *tr = a.d_this + (size_t)rowc * k;
+                            const float xn = yv[p];
+                            const float d = xn - tr[gi];
+                            dpart[p] = d * d;
+                            tr[gi] = xn;
+                            for (int rr = 0; rr < a.n_replicas; rr++)
+                                a.d_replicas[rr][(size_t)(a.replica_row0 + rowc) * k + gi] = xn;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    float v = dpart[p];
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1) v += __shfl_xor_sync(FULL, v, w, 16);
+                    if (r16 == 0) dsum[warp * 4 + 2 * p + hh] = v;
+                }
+            }
+            if (active && len == 0 && nparts == 1) {
+                // empty row: x = 0, no delta (implicit.rs:98-101)
+                float *thisrow = a.d_this + (size_t)row * k;
+                for (int i = lane; i < k; i += 32) {
+                    thisrow[i] = 0.0f;
+                    for (int rr = 0; rr < a.n_replicas; rr++)
+                        a.d_replicas[rr][(size_t)(a.replica_row0 + row) * k + i] = 0.0f;
+                }
+            }
+            prof(5);
+            __syncthreads();  // the workspace aliases the stage rings of the next group
+            if (tid < 4 && ((solve_mask >> tid) & 1u)) {
+                const float t = ((dsum[tid] + dsum[4 + tid]) + dsum[8 + tid]) + dsum[12 + tid];
+                if (t != 0.0f) atomicAdd(a.d_sqdelta, (double)t);
+            }
+            prof(6);
+            continue;
+        }
         const int n_loads = interleave ? 2 : 4;
         for (int p = 0; p < n_loads; p++) {
             if (interleave ? !(gram[2 * p] || gram[2 * p + 1]) : !gram[p]) continue;
@@ -467,19 +668,22 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
     // API returned 1 for the user-half launch on the B200 box, so the design figure is used.)
     int occ = 3;
     if (const char *e = getenv("LK_ALS_TC_OCC")) occ = std::max(1, std::min(3, atoi(e)));  // diagnostics
-    if (a.mode == LK_ALS_IMPLICIT) {
-        auto kern = als_tc_kernel<LK_ALS_IMPLICIT>;
+    // LK_ALS_TCS=0 keeps the per-warp shared-memory solve (diagnostics); default: tensor-core solve
+    bool tcs = interleave != 0;
+    if (const char *e = getenv("LK_ALS_TCS")) tcs = tcs && e[0] != '0';
+    occ = std::max(1, std::min(occ, 512 / (cols + tc::TMEM_Y_COLS)));
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
+    auto launch = [&](auto kern) -> int {
         LK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        occ = std::max(1, std::min(occ, 512 / (cols + tc::TMEM_Y_COLS)));
-        const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
         kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave);
-    } else {
-        auto kern = als_tc_kernel<LK_ALS_EXPLICIT>;
-        LK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        occ = std::max(1, std::min(occ, 512 / (cols + tc::TMEM_Y_COLS)));
-        const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
-        kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave);
-    }
+        return LK_OK;
+    };
+    int rc;
+    if (a.mode == LK_ALS_IMPLICIT)
+        rc = tcs ? launch(als_tc_kernel<LK_ALS_IMPLICIT, true>) : launch(als_tc_kernel<LK_ALS_IMPLICIT, false>);
+    else
+        rc = tcs ? launch(als_tc_kernel<LK_ALS_EXPLICIT, true>) : launch(als_tc_kernel<LK_ALS_EXPLICIT, false>);
+    if (rc != LK_OK) return rc;
     LK_CUDA_TRY(cudaGetLastError());
     return LK_OK;
 }

@@ -1,0 +1,352 @@
+// chol_tc.cuh — blocked Cholesky solve of four 64x64 SPD systems that live in TMEM
+// (role of LAPACK sposv, reference src/accel/als/solve.rs:65-106), with the rank-16
+// trailing updates on the tensor cores.
+//
+// A CTA of 4 warps owns 4 systems as two "pairs": the M=64 accumulator layout puts
+// rows 16w..16w+15 of a system into TMEM lanes 32w..32w+15 (system 2p) or
+// 32w+16..32w+31 (system 2p+1) at columns 64p..64p+63, so warp w can touch block-row
+// w of every system and lane l = 16h + r owns row 16w + r of system 2p + h.
+//
+// Right-looking, block size 16.  Step j (0..3):
+//   1. warp j factors the two 16x16 diagonal blocks per pair in registers (row r in
+//      lane r; pivots and multipliers travel by 16-lane shuffles), carries the
+//      right-hand side along (fused forward substitution), and publishes L_jj^T,
+//      the inverse pivots and z_j in shared memory;
+//   2. warps w > j solve X L_jj^T = A_wj for their rows (one row per lane, L_jj^T
+//      broadcast from shared memory), update their right-hand sides, store X back
+//      into the dead panel columns of TMEM (the back substitution reads it there)
+//      and write X as two tf32 K-major operand tiles: hi = X with the low 13
+//      mantissa bits cleared, lo = X - hi (exact in f32);
+//   3. one thread issues, per system, D[:, 16(j+1):] -= X X^T as three
+//      tcgen05.mma.kind::tf32 (hi.hi + hi.lo + lo.hi, A negated through the
+//      instruction descriptor) — fp32 accumulation in place in TMEM.
+// Back substitution L^T x = z runs block-wise from the bottom: the owners of the
+// already-final x multiply their rows of block column j, a shuffle reduce-scatter
+// sums the 16 lanes, warp j finishes with the transposed triangular solve.
+#pragma once
+
+#include "tc_common.cuh"
+
+namespace lk {
+namespace ctc {
+
+constexpr int LDT = 20;                       // row stride (floats) of a transposed diagonal block
+constexpr int TILE_BYTES = 64 * 16 * 4;       // one operand tile: 64 rows x 16 tf32, K-major, no swizzle
+constexpr int TILES_BYTES = 4 * 2 * TILE_BYTES;          // [system][hi, lo]
+constexpr int LT_FLOATS = 4 * 4 * 16 * LDT;              // [system][step][16][LDT]
+constexpr int INVD_FLOATS = 4 * 64;                      // [system][64]
+constexpr int ZB_FLOATS = 4 * 16;                        // [system][16]
+constexpr int TSUM_FLOATS = 2 * 4 * 4 * 16;              // [parity][warp][system][16]
+constexpr int WS_BYTES = TILES_BYTES + (LT_FLOATS + INVD_FLOATS + ZB_FLOATS + TSUM_FLOATS) * 4 + 16;
+
+// instruction descriptor (mma_sm100_desc.hpp): D f32, A = B = tf32, both K-major, A negated, M = 64; N added at run time
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((64u >> 4) << 24);
+// operand tile address(row, k) = (row / 8) * 512 + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4:
+// core matrix = 8 rows x 16 B; LBO (next core matrix along K) = 128 B, SBO (next 8-row group) = 512 B
+constexpr uint64_t DESC_KMAJOR = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (1ull << 46);
+constexpr uint64_t DESC_KMAJOR_SWAPPED = (uint64_t(512 >> 4) << 16) | (uint64_t(128 >> 4) << 32) | (1ull << 46);
+
+struct Workspace {
+    unsigned char *tiles;  // 128-byte aligned
+    float *lt, *invd, *zb, *tsum;
+    int *bad;              // [4] per-system "pivot not positive" flags
+};
+
+__device__ __forceinline__ Workspace carve(unsigned char *p)
+{
+    Workspace w;
+    w.tiles = p;
+    w.lt = reinterpret_cast<float *>(p + TILES_BYTES);
+    w.invd = w.lt + LT_FLOATS;
+    w.zb = w.invd + INVD_FLOATS;
+    w.tsum = w.zb + ZB_FLOATS;
+    w.bad = reinterpret_cast<int *>(w.tsum + TSUM_FLOATS);
+    return w;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16])
+{
+    uint32_t u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = __uint_as_float(u[i]);
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])),
+          "r"(__float_as_uint(r[3])), "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])),
+          "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])), "r"(__float_as_uint(r[8])),
+          "r"(__float_as_uint(r[9])), "r"(__float_as_uint(r[10])), "r"(__float_as_uint(r[11])),
+          "r"(__float_as_uint(r[12])), "r"(__float_as_uint(r[13])), "r"(__float_as_uint(r[14])),
+          "r"(__float_as_uint(r[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// 32 lanes x 64 consecutive 32-bit columns, registers -> TMEM
+__device__ __forceinline__ void tmem_st64(uint32_t taddr, const uint32_t (&r)[64])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, "
+        "%33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, "
+        "%49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]),
+          "r"(r[32]), "r"(r[33]), "r"(r[34]), "r"(r[35]), "r"(r[36]), "r"(r[37]), "r"(r[38]), "r"(r[39]),
+          "r"(r[40]), "r"(r[41]), "r"(r[42]), "r"(r[43]), "r"(r[44]), "r"(r[45]), "r"(r[46]), "r"(r[47]),
+          "r"(r[48]), "r"(r[49]), "r"(r[50]), "r"(r[51]), "r"(r[52]), "r"(r[53]), "r"(r[54]), "r"(r[55]),
+          "r"(r[56]), "r"(r[57]), "r"(r[58]), "r"(r[59]), "r"(r[60]), "r"(r[61]), "r"(r[62]), "r"(r[63])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+
+__device__ __forceinline__ float rcp_nr(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * fmaf(-x, r, 2.0f);
+}
+
+// Solve the four systems.  On entry the lower triangles of A are in TMEM (tmem_base = column 0 of
+// pair 0, lane field 0) and yv[p] holds the right-hand-side entry of this lane's row of system
+// 2p + (lane >> 4); on exit yv[p] holds the solution entry.  `bar` is an mbarrier (count 1) used
+// only here, `par` its running phase parity.  ws.bad[s] is set when a pivot of system s was not
+// positive (caller zeroes it).  All 128 threads must call.
+template <bool SWAPPED_DESC = false>
+__device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2], const Workspace &ws, uint64_t *bar,
+                                       uint32_t &par, const int tid, long long *prof = nullptr)
+{
+    long long t_prev = prof ? clock64() : 0;
+    auto mark = [&](int i) {
+        if (prof != nullptr && tid == 0) {
+            const long long t = clock64();
+            prof[i] += t - t_prev;
+            t_prev = t;
+        }
+    };
+    const int lane = tid & 31, warp = tid >> 5;
+    const int r = lane & 15, h = lane >> 4;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+    constexpr uint64_t DESC = SWAPPED_DESC ? DESC_KMAJOR_SWAPPED : DESC_KMAJOR;
+
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        if (warp == j) {
+            // ---- diagonal blocks of both pairs, interleaved for ILP ----
+            float a[2][16];
+            tmem_ld16(lane_taddr + 16 * j, a[0]);
+            tmem_ld16(lane_taddr + 64 + 16 * j, a[1]);
+            float inv_mine[2] = {0.0f, 0.0f};
+            bool bad[2] = {false, false};
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    // critical path: pivot broadcast -> reciprocal -> scaled column -> rank-1 update;
+                    // the square-root scaling of L and the right-hand side ride beside it
+                    const float akk = __shfl_sync(FULL, a[p][k], k, 16);
+                    bad[p] |= !(akk > 0.0f);
+                    const float ak = (r >= k) ? a[p][k] : 0.0f;
+                    const float sk = ak * rcp_nr(akk);
+#pragma unroll
+                    for (int c = k + 1; c < 16; c++) {
+                        const float ac = __shfl_sync(FULL, ak, c, 16);
+                        a[p][c] = fmaf(-sk, ac, a[p][c]);
+                    }
+                    const float inv = rsqrt_nr(akk);
+                    const float lk = ak * inv;
+                    a[p][k] = lk;
+                    if (r == k) inv_mine[p] = inv;
+                    const float zk = __shfl_sync(FULL, yv[p], k, 16) * inv;
+                    yv[p] = (r == k) ? zk : fmaf(-lk, zk, yv[p]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const int s = 2 * p + h;
+                float *lt = ws.lt + (s * 4 + j) * 16 * LDT;
+#pragma unroll
+                for (int c = 0; c < 16; c++) lt[c * LDT + r] = a[p][c];  // Lt[c][r] = L[r][c]
+                ws.invd[s * 64 + 16 * j + r] = inv_mine[p];
+                ws.zb[s * 16 + r] = yv[p];
+                if (bad[p] && r == 0) ws.bad[s] = 1;
+            }
+        }
+        if (j == 3) break;
+        __syncthreads();
+        mark(0);
+        if (warp > j) {
+            // both pairs in one pass (two independent dependency chains per lane)
+            float a[2][16];
+            tmem_ld16(lane_taddr + 16 * j, a[0]);
+            tmem_ld16(lane_taddr + 64 + 16 * j, a[1]);
+            float acc[2] = {0.0f, 0.0f};
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const int s = 2 * p + h;
+                    const float *lt = ws.lt + (s * 4 + j) * 16 * LDT;
+                    const float xk = a[p][k] * ws.invd[s * 64 + 16 * j + k];
+                    a[p][k] = xk;
+                    acc[p] = fmaf(xk, ws.zb[s * 16 + k], acc[p]);
+                    // row k of Lt holds L[m][k] for m > k; 16-byte groups m = 4q .. 4q+3
+#pragma unroll
+                    for (int q = (k + 1) / 4; q < 4; q++) {
+                        const float4 t = *reinterpret_cast<const float4 *>(lt + k * LDT + 4 * q);
+                        if (4 * q + 0 > k) a[p][4 * q + 0] = fmaf(-xk, t.x, a[p][4 * q + 0]);
+                        if (4 * q + 1 > k) a[p][4 * q + 1] = fmaf(-xk, t.y, a[p][4 * q + 1]);
+                        if (4 * q + 2 > k) a[p][4 * q + 2] = fmaf(-xk, t.z, a[p][4 * q + 2]);
+                        if (4 * q + 3 > k) a[p][4 * q + 3] = fmaf(-xk, t.w, a[p][4 * q + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const int s = 2 * p + h;
+                yv[p] -= acc[p];
+                tmem_st16(lane_taddr + 64 * p + 16 * j, a[p]);
+                // tf32 operand tiles: hi keeps the top 19 bits, lo = x - hi exactly
+                const int R = 16 * warp + r;
+                unsigned char *thi = ws.tiles + (s * 2) * TILE_BYTES + (R >> 3) * 512 + (R & 7) * 16;
+                unsigned char *tlo = thi + TILE_BYTES;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(a[p][4 * q + 0]) & 0xffffe000u);
+                    hi.y = __uint_as_float(__float_as_uint(a[p][4 * q + 1]) & 0xffffe000u);
+                    hi.z = __uint_as_float(__float_as_uint(a[p][4 * q + 2]) & 0xffffe000u);
+                    hi.w = __uint_as_float(__float_as_uint(a[p][4 * q + 3]) & 0xffffe000u);
+                    lo.x = a[p][4 * q + 0] - hi.x, lo.y = a[p][4 * q + 1] - hi.y;
+                    lo.z = a[p][4 * q + 2] - hi.z, lo.w = a[p][4 * q + 3] - hi.w;
+                    *reinterpret_cast<float4 *>(thi + q * 128) = hi;
+                    *reinterpret_cast<float4 *>(tlo + q * 128) = lo;
+                }
+            }
+        }
+        fence_proxy_async();
+        tmem_fence_before();
+        __syncthreads();
+        mark(1);
+        if (tid == 0) {
+            tmem_fence_after();
+            const int c0 = 16 * (j + 1);
+            const uint32_t idesc = IDESC_TF32 | ((uint32_t)((64 - c0) >> 3) << 17);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint32_t d = tmem_base + ((uint32_t)((s & 1) * 16) << 16) + (uint32_t)((s >> 1) * 64 + c0);
+                const uint32_t hi = smem_u32(ws.tiles + (s * 2) * TILE_BYTES);
+                const uint32_t lo = hi + TILE_BYTES;
+                const uint32_t boff = (uint32_t)(c0 >> 3) * 512;  // B starts at row c0
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+                    const uint64_t a_hi = DESC | (uint64_t)(((hi + kk * 256) >> 4) & 0x3fffu);
+                    const uint64_t a_lo = DESC | (uint64_t)(((lo + kk * 256) >> 4) & 0x3fffu);
+                    const uint64_t b_hi = DESC | (uint64_t)(((hi + boff + kk * 256) >> 4) & 0x3fffu);
+                    const uint64_t b_lo = DESC | (uint64_t)(((lo + boff + kk * 256) >> 4) & 0x3fffu);
+                    umma_tf32(d, a_hi, b_hi, idesc);
+                    umma_tf32(d, a_hi, b_lo, idesc);
+                    umma_tf32(d, a_lo, b_hi, idesc);
+                }
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, par);
+        par ^= 1u;
+        tmem_fence_after();
+        mark(2);
+    }
+
+    // ---- back substitution L^T x = z; yv holds z ----
+#pragma unroll 1
+    for (int j = 3; j >= 0; j--) {
+        float *ts = ws.tsum + (j & 1) * (4 * 4 * 16);
+        if (warp > j) {
+            float v[2][16];
+            tmem_ld16(lane_taddr + 16 * j, v[0]);
+            tmem_ld16(lane_taddr + 64 + 16 * j, v[1]);
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+#pragma unroll
+                for (int c = 0; c < 16; c++) v[p][c] *= yv[p];
+            // reduce-scatter over the 16 lanes of each half: lane r ends with column r
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1) {
+                const bool up = (r & w) != 0;
+#pragma unroll
+                for (int i = 0; i < w; i++) {
+#pragma unroll
+                    for (int p = 0; p < 2; p++) {
+                        const float send = up ? v[p][i] : v[p][i + w];
+                        const float keep = up ? v[p][i + w] : v[p][i];
+                        v[p][i] = keep + __shfl_xor_sync(FULL, send, w, 16);
+                    }
+                }
+            }
+            ts[(warp * 4 + h) * 16 + r] = v[0][0];
+            ts[(warp * 4 + 2 + h) * 16 + r] = v[1][0];
+        }
+        __syncthreads();
+        if (warp == j) {
+            float rhs[2], inv[2], lrow[2][16];
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const int s = 2 * p + h;
+                rhs[p] = yv[p];
+                for (int w = j + 1; w < 4; w++) rhs[p] -= ts[(w * 4 + s) * 16 + r];
+                const float *lt = ws.lt + ((s * 4 + j) * 16 + r) * LDT;  // Lt[r][k] = L[k][r]
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(lt + 4 * q);
+                    lrow[p][4 * q] = t.x, lrow[p][4 * q + 1] = t.y, lrow[p][4 * q + 2] = t.z, lrow[p][4 * q + 3] = t.w;
+                }
+                inv[p] = ws.invd[s * 64 + 16 * j + r];
+            }
+#pragma unroll
+            for (int k = 15; k >= 0; k--) {
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const float xk = __shfl_sync(FULL, rhs[p] * inv[p], k, 16);
+                    if (r < k)
+                        rhs[p] = fmaf(-lrow[p][k], xk, rhs[p]);
+                    else if (r == k)
+                        rhs[p] = xk;
+                }
+            }
+            yv[0] = rhs[0];
+            yv[1] = rhs[1];
+        }
+    }
+    if (prof != nullptr) {
+        __syncthreads();
+        mark(3);
+    }
+}
+
+}  // namespace ctc
+}  // namespace lk
