@@ -73,13 +73,17 @@ using tcd::DESC_LBO;
 // TCS: the systems stay in TMEM and are solved by the blocked tensor-core Cholesky (chol_tc.cuh,
 // requires the interleaved allocation); otherwise they are drained to shared memory and solved
 // by one warp each (als_common.cuh).
-template <int MODE, bool TCS>
+// GJ (with TCS): block Gauss-Jordan variant of the tensor-core solve (chol_tc.cuh).
+template <int MODE, bool TCS, bool GJ = false>
 __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const int interleave)
 {
     using namespace tc;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the warp index goes through a shuffle so that the compiler knows it is warp-uniform: addresses
+    // and descriptors derived from it then live in uniform registers and the tcgen05.mma issue needs
+    // no per-instruction broadcast
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(FULL, tid >> 5, 0);
 
     unsigned char *wreg = base + warp * WARP_BYTES;  // this warp's stage ring, later its 64x68 system
     float *As = reinterpret_cast<float *>(wreg);
@@ -101,7 +105,8 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     constexpr int k = KP;
 
     if (tid == 0) {
-        for (int i = 0; i < WARPS * NSTAGE + WARPS + 1; i++) mbar_init(&bars[i], 1);
+        for (int i = 0; i < WARPS * NSTAGE + WARPS; i++) mbar_init(&bars[i], 1);
+        mbar_init(solve_bar, 4);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -147,11 +152,32 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     uint32_t full_par = 0;  // bit c: parity of the number of commits seen on acc_full[c]
     uint32_t solve_par = 0;
 
+    // Tensor-core solve, implicit mode: the accumulators start every group holding OtOr / v, the Gram
+    // MMAs accumulate on top, and the finished accumulator is A / v — the drain pass (read 64x64,
+    // fma with OtOr, write back) disappears.  Warp w writes rows 16w..16w+15 of all four systems.
+    constexpr bool PRELOAD = TCS && MODE == LK_ALS_IMPLICIT;
+    auto preload_otor = [&]() {
+        const float rv = 1.0f / a.uniform_val;
+        const float4 *ot = reinterpret_cast<const float4 *>(a.d_otor + (16 * warp + (lane & 15)) * k);
+        uint32_t r[64];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const float4 o = __ldg(ot + q);
+            r[4 * q + 0] = __float_as_uint(o.x * rv), r[4 * q + 1] = __float_as_uint(o.y * rv);
+            r[4 * q + 2] = __float_as_uint(o.z * rv), r[4 * q + 3] = __float_as_uint(o.w * rv);
+        }
+        const uint32_t t = tmem_base + ((uint32_t)(32 * warp) << 16);
+        ctc::tmem_st64(t, r);
+        ctc::tmem_st64(t + 64u, r);
+        tmem_fence_before();
+    };
+    if constexpr (PRELOAD) preload_otor();
+
     // the index of the next group is fetched one group ahead (during the solve phase)
     if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);
     __syncthreads();
     for (;;) {
-        const int64_t g = s_misc[0];
+        const int64_t g = __shfl_sync(FULL, s_misc[0], 0);
         __syncthreads();
         if (g * WARPS >= a.n_chunks) break;
         prof(0);
@@ -164,6 +190,10 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             row = c0.x, begin = c0.y, len = c0.z, nparts = c0.w;
             slot0 = c1.x, part = c1.y, split_idx = c1.z;
         }
+        // same value in every lane — say so (see `warp` above)
+        row = __shfl_sync(FULL, row, 0), begin = __shfl_sync(FULL, begin, 0), len = __shfl_sync(FULL, len, 0);
+        nparts = __shfl_sync(FULL, nparts, 0), slot0 = __shfl_sync(FULL, slot0, 0);
+        part = __shfl_sync(FULL, part, 0), split_idx = __shfl_sync(FULL, split_idx, 0);
         const bool has_gram = active && len > 0;
         int n_row = 0;
         if (active) n_row = __ldg(a.d_indptr + row + 1) - __ldg(a.d_indptr + row);
@@ -255,14 +285,14 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                         __syncwarp();
                         const int nrows = min(STAGE_ROWS, len - it * STAGE_ROWS);
                         // 3. tensor cores: 16 rows per instruction
-                        if (lane == 0) {
+                        if (ctc::elect_one()) {
                             tmem_fence_after();
                             const uint32_t sbase = smem_u32(wreg + s * STAGE_BYTES);
                             const int nk = (nrows + 15) >> 4;
                             for (int kk = 0; kk < nk; kk++) {
                                 const uint64_t desc =
                                     DESC_HI | DESC_LBO | (uint64_t)(((sbase + kk * 2048) >> 4) & 0x3fffu);
-                                umma_bf16_64x64x16(my_acc, desc, (it > 0 || kk > 0) ? 1u : 0u);
+                                umma_bf16_64x64x16(my_acc, desc, (PRELOAD || it > 0 || kk > 0) ? 1u : 0u);
                                 if (ymma) umma_bf16_ab(my_yacc, desc, ydesc, IDESC_Y, (it > 0 || kk > 0) ? 1u : 0u);
                             }
                             umma_commit(&stage_free[s]);
@@ -334,23 +364,17 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 if (!(gram[2 * p] || gram[2 * p + 1])) continue;
+                if constexpr (MODE == LK_ALS_IMPLICIT) {
+                    // the accumulators were preloaded with OtOr / v (preload_otor): unsplit rows are
+                    // complete as they stand — the system solved is (A / v) x = y / v
+                    if (!((gram[2 * p] && parts[2 * p] > 1) || (gram[2 * p + 1] && parts[2 * p + 1] > 1))) continue;
+                }
                 const int c = 2 * p + hh;
                 uint32_t r[64];
                 tmem_ld_32x32b_x64(lane_taddr + (uint32_t)(p * 64), r);
                 if (gram[c]) {
                     if (parts[c] == 1) {
-                        if constexpr (MODE == LK_ALS_IMPLICIT) {
-                            const float v = a.uniform_val;
-                            const float4 *ot = reinterpret_cast<const float4 *>(a.d_otor + gi * k);
-#pragma unroll
-                            for (int q = 0; q < 16; q++) {
-                                const float4 o = __ldg(ot + q);
-                                r[4 * q + 0] = __float_as_uint(fmaf(v, __uint_as_float(r[4 * q + 0]), o.x));
-                                r[4 * q + 1] = __float_as_uint(fmaf(v, __uint_as_float(r[4 * q + 1]), o.y));
-                                r[4 * q + 2] = __float_as_uint(fmaf(v, __uint_as_float(r[4 * q + 2]), o.z));
-                                r[4 * q + 3] = __float_as_uint(fmaf(v, __uint_as_float(r[4 * q + 3]), o.w));
-                            }
-                        } else {
+                        if constexpr (MODE == LK_ALS_EXPLICIT) {
                             const float regn = a.reg * (float)nrowc[c];
 #pragma unroll
                             for (int i = 0; i < 64; i++)
@@ -365,11 +389,14 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                                                __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
                     }
                 }
-                if ((gram[2 * p] && parts[2 * p] == 1) || (gram[2 * p + 1] && parts[2 * p + 1] == 1))
+                if (MODE == LK_ALS_EXPLICIT &&
+                    ((gram[2 * p] && parts[2 * p] == 1) || (gram[2 * p + 1] && parts[2 * p + 1] == 1)))
                     ctc::tmem_st64(lane_taddr + (uint32_t)(p * 64), r);
             }
             if (ymma) {
+                // unsplit rows: y / v (see above); partial slots keep the unscaled (v + 1) * column sums
                 const float w1 = a.uniform_val + 1.0f;
+                const float rv = 1.0f / a.uniform_val;
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
                     if (!(gram[2 * p] || gram[2 * p + 1])) continue;
@@ -379,7 +406,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                     if (gram[c]) {
                         const float yy = w1 * __uint_as_float(ry[0]);
                         if (parts[c] == 1)
-                            yv[p] = yy;
+                            yv[p] = yy * rv;
                         else
                             __stcg(a.d_partials + (size_t)slotc[c] * SLOTF + KP * KP + gi, yy);
                     }
@@ -427,10 +454,11 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                                 sacc.x += t.x, sacc.y += t.y, sacc.z += t.z, sacc.w += t.w;
                             }
                             if constexpr (MODE == LK_ALS_IMPLICIT) {
+                                // every part carries one copy of the preloaded OtOr / v: keep exactly one
                                 const float4 o = __ldg(reinterpret_cast<const float4 *>(a.d_otor + gi * k) + q);
-                                const float v = a.uniform_val;
-                                sacc.x = fmaf(v, sacc.x, o.x), sacc.y = fmaf(v, sacc.y, o.y);
-                                sacc.z = fmaf(v, sacc.z, o.z), sacc.w = fmaf(v, sacc.w, o.w);
+                                const float extra = (float)(parts[c] - 1) / a.uniform_val;
+                                sacc.x = fmaf(-extra, o.x, sacc.x), sacc.y = fmaf(-extra, o.y, sacc.y);
+                                sacc.z = fmaf(-extra, o.z, sacc.z), sacc.w = fmaf(-extra, o.w, sacc.w);
                             } else {
                                 if (4 * q + 0 == gi) sacc.x += regn;
                                 if (4 * q + 1 == gi) sacc.y += regn;
@@ -443,7 +471,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                         float sy = 0.0f;
                         for (int pp = 0; pp < parts[c]; pp++)
                             sy += __ldcg(a.d_partials + (size_t)(slot0c + pp) * SLOTF + KP * KP + gi);
-                        yv[p] = sy;
+                        yv[p] = (MODE == LK_ALS_IMPLICIT) ? sy / a.uniform_val : sy;
                     }
                     ctc::tmem_st64(lane_taddr + (uint32_t)(p * 64), r);
                     solve_mask |= 1u << c;
@@ -456,7 +484,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             // ------------------------------------------------------------------
             if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);  // next group, read after the closing barrier
             if (solve_mask) {
-                ctc::solve4(tmem_base, yv, ws, solve_bar, solve_par, tid);
+                ctc::solve4<false, GJ>(tmem_base, yv, ws, solve_bar, solve_par, tid);
                 __syncthreads();  // pivot flags
                 float dpart[2] = {0.0f, 0.0f};
 #pragma unroll
@@ -494,6 +522,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                         a.d_replicas[rr][(size_t)(a.replica_row0 + row) * k + i] = 0.0f;
                 }
             }
+            if constexpr (PRELOAD) preload_otor();  // accumulators of the next group (this warp's rows)
             prof(5);
             __syncthreads();  // the workspace aliases the stage rings of the next group
             if (tid < 4 && ((solve_mask >> tid) & 1u)) {
@@ -671,6 +700,8 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
     // LK_ALS_TCS=0 keeps the per-warp shared-memory solve (diagnostics); default: tensor-core solve
     bool tcs = interleave != 0;
     if (const char *e = getenv("LK_ALS_TCS")) tcs = tcs && e[0] != '0';
+    // the tensor-core path solves (A / v) x = y / v: not for a zero confidence weight
+    if (a.mode == LK_ALS_IMPLICIT && !(fabsf(a.uniform_val) > 1e-20f)) tcs = false;
     occ = std::max(1, std::min(occ, 512 / (cols + tc::TMEM_Y_COLS)));
     const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
     auto launch = [&](auto kern) -> int {
@@ -678,11 +709,18 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
         kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave);
         return LK_OK;
     };
+    // LK_ALS_GJ=1: block Gauss-Jordan instead of blocked Cholesky + block back substitution (experiment)
+    bool gj = false;
+    if (const char *e = getenv("LK_ALS_GJ")) gj = e[0] != '0';
     int rc;
     if (a.mode == LK_ALS_IMPLICIT)
-        rc = tcs ? launch(als_tc_kernel<LK_ALS_IMPLICIT, true>) : launch(als_tc_kernel<LK_ALS_IMPLICIT, false>);
+        rc = !tcs  ? launch(als_tc_kernel<LK_ALS_IMPLICIT, false>)
+             : gj  ? launch(als_tc_kernel<LK_ALS_IMPLICIT, true, true>)
+                   : launch(als_tc_kernel<LK_ALS_IMPLICIT, true, false>);
     else
-        rc = tcs ? launch(als_tc_kernel<LK_ALS_EXPLICIT, true>) : launch(als_tc_kernel<LK_ALS_EXPLICIT, false>);
+        rc = !tcs  ? launch(als_tc_kernel<LK_ALS_EXPLICIT, false>)
+             : gj  ? launch(als_tc_kernel<LK_ALS_EXPLICIT, true, true>)
+                   : launch(als_tc_kernel<LK_ALS_EXPLICIT, true, false>);
     if (rc != LK_OK) return rc;
     LK_CUDA_TRY(cudaGetLastError());
     return LK_OK;

@@ -33,11 +33,13 @@ namespace ctc {
 constexpr int LDT = 20;                       // row stride (floats) of a transposed diagonal block
 constexpr int TILE_BYTES = 64 * 16 * 4;       // one operand tile: 64 rows x 16 tf32, K-major, no swizzle
 constexpr int TILES_BYTES = 4 * 2 * TILE_BYTES;          // [system][hi, lo]
-constexpr int LT_FLOATS = 4 * 4 * 16 * LDT;              // [system][step][16][LDT]
+constexpr int LT_FLOATS = 4 * 16 * LDT;                  // [system][16][LDT]: L_jj^T of the current step
+constexpr int LD_FLOATS = 4 * 4 * 16 * LDT;              // [system][step][16][LDT]: L_jj, kept for the back substitution
 constexpr int INVD_FLOATS = 4 * 64;                      // [system][64]
 constexpr int ZB_FLOATS = 4 * 16;                        // [system][16]
-constexpr int TSUM_FLOATS = 2 * 4 * 4 * 16;              // [parity][warp][system][16]
-constexpr int WS_BYTES = TILES_BYTES + (LT_FLOATS + INVD_FLOATS + ZB_FLOATS + TSUM_FLOATS) * 4 + 16;
+constexpr int TSUM_FLOATS = 4 * 4 * 4 * 16;              // [block row][block column][system][16]
+constexpr int WS_BYTES =
+    TILES_BYTES + (LT_FLOATS + LD_FLOATS + INVD_FLOATS + ZB_FLOATS + TSUM_FLOATS) * 4 + 16;
 
 // instruction descriptor (mma_sm100_desc.hpp): D f32, A = B = tf32, both K-major, A negated, M = 64; N added at run time
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((64u >> 4) << 24);
@@ -48,7 +50,7 @@ constexpr uint64_t DESC_KMAJOR_SWAPPED = (uint64_t(512 >> 4) << 16) | (uint64_t(
 
 struct Workspace {
     unsigned char *tiles;  // 128-byte aligned
-    float *lt, *invd, *zb, *tsum;
+    float *lt, *ld, *invd, *zb, *tsum;
     int *bad;              // [4] per-system "pivot not positive" flags
 };
 
@@ -57,7 +59,8 @@ __device__ __forceinline__ Workspace carve(unsigned char *p)
     Workspace w;
     w.tiles = p;
     w.lt = reinterpret_cast<float *>(p + TILES_BYTES);
-    w.invd = w.lt + LT_FLOATS;
+    w.ld = w.lt + LT_FLOATS;
+    w.invd = w.ld + LD_FLOATS;
     w.zb = w.invd + INVD_FLOATS;
     w.tsum = w.zb + ZB_FLOATS;
     w.bad = reinterpret_cast<int *>(w.tsum + TSUM_FLOATS);
@@ -125,28 +128,73 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
-__device__ __forceinline__ float rcp_nr(float x)
+// MUFU.RCP alone (max relative error 2^-23, the size of an f32 rounding): it sits on the pivot
+// chain of the diagonal blocks, where a Newton step would cost two more dependent operations
+__device__ __forceinline__ float rcp_fast(float x)
 {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r * fmaf(-x, r, 2.0f);
+    return r;
+}
+
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// non-blocking probe of an mbarrier phase (the waiting warp polls: try_wait parks the thread and
+// was measured to wake it ~1 k cycles late)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 
 // Solve the four systems.  On entry the lower triangles of A are in TMEM (tmem_base = column 0 of
 // pair 0, lane field 0) and yv[p] holds the right-hand-side entry of this lane's row of system
-// 2p + (lane >> 4); on exit yv[p] holds the solution entry.  `bar` is an mbarrier (count 1) used
+// 2p + (lane >> 4); on exit yv[p] holds the solution entry.  `bar` is an mbarrier (count 4: one commit per warp) used
 // only here, `par` its running phase parity.  ws.bad[s] is set when a pivot of system s was not
 // positive (caller zeroes it).  All 128 threads must call.
-template <bool SWAPPED_DESC = false>
+//
+// GJ = true turns the block elimination into a block Gauss-Jordan: at step j *every* other block
+// row w (above the pivot block as well as below) gets X_w = A_wj L_jj^-T, the tensor cores update
+// all 64 rows (they do anyway: M = 64), the right-hand sides of all rows lose X_w z_j, and the pivot
+// block row itself is left alone (its operand-tile rows are zeroed).  After four steps the system
+// is block diagonal with the pivot blocks L_jj L_jj^T, so every warp finishes its own 16 unknowns
+// at the same time — no serial block back substitution.  Measured error vs Cholesky: see DESIGN.md.
+template <bool SWAPPED_DESC = false, bool GJ = false>
 __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2], const Workspace &ws, uint64_t *bar,
                                        uint32_t &par, const int tid, long long *prof = nullptr)
 {
     long long t_prev = prof ? clock64() : 0;
-    auto mark = [&](int i) {
+    auto mark = [&](int i, int step = -1) {  // thread 0's view; per-step copies at prof[16 + 4 * i + step]
         if (prof != nullptr && tid == 0) {
             const long long t = clock64();
             prof[i] += t - t_prev;
+            if (step >= 0) prof[16 + 4 * i + step] += t - t_prev;
             t_prev = t;
+        }
+    };
+    long long t_prev3 = t_prev;
+    auto mark3 = [&](int i) {  // warp 3's view (it runs the triangular solve of every step)
+        if (prof != nullptr && tid == 96) {
+            const long long t = clock64();
+            prof[i] += t - t_prev3;
+            t_prev3 = t;
         }
     };
     const int lane = tid & 31, warp = tid >> 5;
@@ -163,6 +211,7 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
             tmem_ld16(lane_taddr + 64 + 16 * j, a[1]);
             float inv_mine[2] = {0.0f, 0.0f};
             bool bad[2] = {false, false};
+            float zt[2] = {yv[0], yv[1]};  // becomes z_j = L_jj^-1 y_j
 #pragma unroll
             for (int k = 0; k < 16; k++) {
 #pragma unroll
@@ -172,7 +221,7 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
                     const float akk = __shfl_sync(FULL, a[p][k], k, 16);
                     bad[p] |= !(akk > 0.0f);
                     const float ak = (r >= k) ? a[p][k] : 0.0f;
-                    const float sk = ak * rcp_nr(akk);
+                    const float sk = ak * rcp_fast(akk);
 #pragma unroll
                     for (int c = k + 1; c < 16; c++) {
                         const float ac = __shfl_sync(FULL, ak, c, 16);
@@ -182,43 +231,88 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
                     const float lk = ak * inv;
                     a[p][k] = lk;
                     if (r == k) inv_mine[p] = inv;
-                    const float zk = __shfl_sync(FULL, yv[p], k, 16) * inv;
-                    yv[p] = (r == k) ? zk : fmaf(-lk, zk, yv[p]);
+                    const float zk = __shfl_sync(FULL, zt[p], k, 16) * inv;
+                    zt[p] = (r == k) ? zk : fmaf(-lk, zk, zt[p]);
                 }
+            }
+            if constexpr (!GJ) {  // Cholesky: the right-hand side continues as z; Gauss-Jordan keeps y
+                yv[0] = zt[0];
+                yv[1] = zt[1];
             }
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 const int s = 2 * p + h;
-                float *lt = ws.lt + (s * 4 + j) * 16 * LDT;
+                float *lt = ws.lt + s * 16 * LDT;
 #pragma unroll
                 for (int c = 0; c < 16; c++) lt[c * LDT + r] = a[p][c];  // Lt[c][r] = L[r][c]
+                float *ldr = ws.ld + ((s * 4 + j) * 16 + r) * LDT;       // row r of L_jj
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    *reinterpret_cast<float4 *>(ldr + 4 * q) =
+                        make_float4(a[p][4 * q], a[p][4 * q + 1], a[p][4 * q + 2], a[p][4 * q + 3]);
                 ws.invd[s * 64 + 16 * j + r] = inv_mine[p];
-                ws.zb[s * 16 + r] = yv[p];
+                ws.zb[s * 16 + r] = zt[p];
                 if (bad[p] && r == 0) ws.bad[s] = 1;
+                if constexpr (GJ) {
+                    if (j < 3) {  // the pivot block row takes no part in this step's update
+                        const int R = 16 * warp + r;
+                        unsigned char *thi = ws.tiles + (s * 2) * TILE_BYTES + (R >> 3) * 512 + (R & 7) * 16;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            *reinterpret_cast<float4 *>(thi + q * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            *reinterpret_cast<float4 *>(thi + TILE_BYTES + q * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
             }
         }
-        if (j == 3) break;
+        if (!GJ && j == 3) break;
+        tmem_fence_before();
         __syncthreads();
-        mark(0);
-        if (warp > j) {
+        tmem_fence_after();
+        mark(0, j);
+        mark3(4);
+        if (GJ ? (warp != j) : (warp > j)) {
             // both pairs in one pass (two independent dependency chains per lane)
             float a[2][16];
             tmem_ld16(lane_taddr + 16 * j, a[0]);
             tmem_ld16(lane_taddr + 64 + 16 * j, a[1]);
-            float acc[2] = {0.0f, 0.0f};
+            mark3(5);
+            float iv[2][16];
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const int s = 2 * p + h;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(ws.invd + s * 64 + 16 * j + 4 * q);
+                    iv[p][4 * q] = t.x, iv[p][4 * q + 1] = t.y, iv[p][4 * q + 2] = t.z, iv[p][4 * q + 3] = t.w;
+                }
+            }
+            // row k of Lt holds L[m][k] for m > k in 16-byte groups m = 4q .. 4q+3; the rows are
+            // fetched one step ahead of their use so that no shared-memory latency sits on the chain
+            float4 row[2][2][4];
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    row[0][p][q] = *reinterpret_cast<const float4 *>(ws.lt + (2 * p + h) * 16 * LDT + 4 * q);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
+                if (k + 1 < 16) {
+#pragma unroll
+                    for (int p = 0; p < 2; p++)
+#pragma unroll
+                        for (int q = (k + 2) / 4; q < 4; q++)
+                            row[(k + 1) & 1][p][q] = *reinterpret_cast<const float4 *>(
+                                ws.lt + (2 * p + h) * 16 * LDT + (k + 1) * LDT + 4 * q);
+                }
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
-                    const int s = 2 * p + h;
-                    const float *lt = ws.lt + (s * 4 + j) * 16 * LDT;
-                    const float xk = a[p][k] * ws.invd[s * 64 + 16 * j + k];
+                    const float xk = a[p][k] * iv[p][k];
                     a[p][k] = xk;
-                    acc[p] = fmaf(xk, ws.zb[s * 16 + k], acc[p]);
-                    // row k of Lt holds L[m][k] for m > k; 16-byte groups m = 4q .. 4q+3
 #pragma unroll
                     for (int q = (k + 1) / 4; q < 4; q++) {
-                        const float4 t = *reinterpret_cast<const float4 *>(lt + k * LDT + 4 * q);
+                        const float4 t = row[k & 1][p][q];
                         if (4 * q + 0 > k) a[p][4 * q + 0] = fmaf(-xk, t.x, a[p][4 * q + 0]);
                         if (4 * q + 1 > k) a[p][4 * q + 1] = fmaf(-xk, t.y, a[p][4 * q + 1]);
                         if (4 * q + 2 > k) a[p][4 * q + 2] = fmaf(-xk, t.z, a[p][4 * q + 2]);
@@ -226,11 +320,26 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
                     }
                 }
             }
+            mark3(6);
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 const int s = 2 * p + h;
-                yv[p] -= acc[p];
-                tmem_st16(lane_taddr + 64 * p + 16 * j, a[p]);
+                // right-hand side: y_R -= X[R][:] . z_j (two partial sums)
+                float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 u = *reinterpret_cast<const float4 *>(ws.zb + s * 16 + 4 * q);
+                    acc0 = fmaf(a[p][4 * q + 0], u.x, acc0);
+                    acc1 = fmaf(a[p][4 * q + 1], u.y, acc1);
+                    acc0 = fmaf(a[p][4 * q + 2], u.z, acc0);
+                    acc1 = fmaf(a[p][4 * q + 3], u.w, acc1);
+                }
+                yv[p] -= acc0 + acc1;
+                if constexpr (GJ) {
+                    if (j == 3) continue;  // last step: no trailing columns left, only the right-hand sides
+                } else {
+                    tmem_st16(lane_taddr + 64 * p + 16 * j, a[p]);  // the back substitution reads it there
+                }
                 // tf32 operand tiles: hi keeps the top 19 bits, lo = x - hi exactly
                 const int R = 16 * warp + r;
                 unsigned char *thi = ws.tiles + (s * 2) * TILE_BYTES + (R >> 3) * 512 + (R & 7) * 16;
@@ -249,16 +358,24 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
                 }
             }
         }
+        mark3(7);
+        if (GJ && j == 3) break;
         fence_proxy_async();
         tmem_fence_before();
         __syncthreads();
-        mark(1);
-        if (tid == 0) {
+        mark(1, j);
+        mark3(8);
+        // lane 0 of warp s issues the six MMAs of system s and commits them (the barrier counts 4
+        // arrivals); its sibling lanes wait at the __syncwarp so their spinning cannot starve it
+        // (the warp index is re-derived through a shuffle so that the compiler knows it is uniform
+        // and keeps the descriptors in uniform registers instead of broadcasting them per MMA)
+        const int warp_u = __shfl_sync(FULL, warp, 0);
+        if (elect_one()) {
             tmem_fence_after();
             const int c0 = 16 * (j + 1);
             const uint32_t idesc = IDESC_TF32 | ((uint32_t)((64 - c0) >> 3) << 17);
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
+            {
+                const int s = warp_u;
                 const uint32_t d = tmem_base + ((uint32_t)((s & 1) * 16) << 16) + (uint32_t)((s >> 1) * 64 + c0);
                 const uint32_t hi = smem_u32(ws.tiles + (s * 2) * TILE_BYTES);
                 const uint32_t lo = hi + TILE_BYTES;
@@ -276,71 +393,126 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
             }
             umma_commit(bar);
         }
-        mbar_wait(bar, par);
+        __syncwarp();
+        // only the warp that factors the next diagonal block needs the updated accumulators now;
+        // the others meet it at the barrier after that factorisation
+        if (warp == j + 1) {
+            while (!mbar_test(bar, par)) {
+            }
+            tmem_fence_after();
+        }
         par ^= 1u;
-        tmem_fence_after();
-        mark(2);
+        mark(2, j);
+        mark3(9);
+    }
+
+    if constexpr (GJ) {
+        // block-diagonal system left: L_ww L_ww^T x_w = y_w — every warp solves its own two pairs
+        float rowl[2][16], coll[2][16], inv[2];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const int s = 2 * p + h;
+            const float *ldw = ws.ld + (s * 4 + warp) * 16 * LDT;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 t = *reinterpret_cast<const float4 *>(ldw + r * LDT + 4 * q);  // L[r][k], k < r
+                rowl[p][4 * q] = t.x, rowl[p][4 * q + 1] = t.y, rowl[p][4 * q + 2] = t.z, rowl[p][4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) coll[p][k] = ldw[k * LDT + r];  // L[k][r], k > r
+            inv[p] = ws.invd[s * 64 + 16 * warp + r];
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const float zk = __shfl_sync(FULL, yv[p] * inv[p], k, 16);
+                yv[p] = (r == k) ? zk : ((r > k) ? fmaf(-rowl[p][k], zk, yv[p]) : yv[p]);
+            }
+        }
+#pragma unroll
+        for (int k = 15; k >= 0; k--) {
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const float xk = __shfl_sync(FULL, yv[p] * inv[p], k, 16);
+                yv[p] = (r == k) ? xk : ((r < k) ? fmaf(-coll[p][k], xk, yv[p]) : yv[p]);
+            }
+        }
+        if (prof != nullptr) {
+            __syncthreads();
+            mark(3);
+        }
+        return;
     }
 
     // ---- back substitution L^T x = z; yv holds z ----
-#pragma unroll 1
-    for (int j = 3; j >= 0; j--) {
-        float *ts = ws.tsum + (j & 1) * (4 * 4 * 16);
-        if (warp > j) {
-            float v[2][16];
-            tmem_ld16(lane_taddr + 16 * j, v[0]);
-            tmem_ld16(lane_taddr + 64 + 16 * j, v[1]);
+    // ts[(w*4 + jj)*4 + s][c]: what block row w (its x final) takes off the right-hand side of block jj.
+    // Step j: warp j finishes x_j, multiplies its rows of block column j-1 (the only contribution the
+    // next step is still missing) before the barrier and the older block columns after it, in the
+    // shadow of warp j-1's solve.
+    auto contribute = [&](const int jj) {
+        float v[2][16];
+        tmem_ld16(lane_taddr + 16 * jj, v[0]);
+        tmem_ld16(lane_taddr + 64 + 16 * jj, v[1]);
 #pragma unroll
-            for (int p = 0; p < 2; p++)
+        for (int p = 0; p < 2; p++)
 #pragma unroll
-                for (int c = 0; c < 16; c++) v[p][c] *= yv[p];
-            // reduce-scatter over the 16 lanes of each half: lane r ends with column r
+            for (int c = 0; c < 16; c++) v[p][c] *= yv[p];
+        // reduce-scatter over the 16 lanes of each half: lane r ends with column r
 #pragma unroll
-            for (int w = 8; w >= 1; w >>= 1) {
-                const bool up = (r & w) != 0;
+        for (int w = 8; w >= 1; w >>= 1) {
+            const bool up = (r & w) != 0;
 #pragma unroll
-                for (int i = 0; i < w; i++) {
+            for (int i = 0; i < w; i++) {
 #pragma unroll
-                    for (int p = 0; p < 2; p++) {
-                        const float send = up ? v[p][i] : v[p][i + w];
-                        const float keep = up ? v[p][i + w] : v[p][i];
-                        v[p][i] = keep + __shfl_xor_sync(FULL, send, w, 16);
-                    }
+                for (int p = 0; p < 2; p++) {
+                    const float send = up ? v[p][i] : v[p][i + w];
+                    const float keep = up ? v[p][i + w] : v[p][i];
+                    v[p][i] = keep + __shfl_xor_sync(FULL, send, w, 16);
                 }
             }
-            ts[(warp * 4 + h) * 16 + r] = v[0][0];
-            ts[(warp * 4 + 2 + h) * 16 + r] = v[1][0];
         }
-        __syncthreads();
+        ws.tsum[((warp * 4 + jj) * 4 + h) * 16 + r] = v[0][0];
+        ws.tsum[((warp * 4 + jj) * 4 + 2 + h) * 16 + r] = v[1][0];
+    };
+#pragma unroll 1
+    for (int j = 3; j >= 0; j--) {
         if (warp == j) {
-            float rhs[2], inv[2], lrow[2][16];
+            // every lane solves the whole 16x16 transposed system of its half redundantly: the
+            // right-hand side is broadcast once, then no shuffle sits on the dependency chain
+            float x[2][16];
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 const int s = 2 * p + h;
-                rhs[p] = yv[p];
-                for (int w = j + 1; w < 4; w++) rhs[p] -= ts[(w * 4 + s) * 16 + r];
-                const float *lt = ws.lt + ((s * 4 + j) * 16 + r) * LDT;  // Lt[r][k] = L[k][r]
+                float rhs = yv[p];
+                for (int w = j + 1; w < 4; w++) rhs -= ws.tsum[((w * 4 + j) * 4 + s) * 16 + r];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const float4 t = *reinterpret_cast<const float4 *>(lt + 4 * q);
-                    lrow[p][4 * q] = t.x, lrow[p][4 * q + 1] = t.y, lrow[p][4 * q + 2] = t.z, lrow[p][4 * q + 3] = t.w;
-                }
-                inv[p] = ws.invd[s * 64 + 16 * j + r];
+                for (int k = 0; k < 16; k++) x[p][k] = __shfl_sync(FULL, rhs, k, 16);
             }
 #pragma unroll
             for (int k = 15; k >= 0; k--) {
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
-                    const float xk = __shfl_sync(FULL, rhs[p] * inv[p], k, 16);
-                    if (r < k)
-                        rhs[p] = fmaf(-lrow[p][k], xk, rhs[p]);
-                    else if (r == k)
-                        rhs[p] = xk;
+                    const int s = 2 * p + h;
+                    const float *ldk = ws.ld + ((s * 4 + j) * 16 + k) * LDT;  // row k of L_jj: L[k][m], m < k
+                    const float xk = x[p][k] * ws.invd[s * 64 + 16 * j + k];
+                    if (r == k) yv[p] = xk;
+#pragma unroll
+                    for (int q = 0; 4 * q < k; q++) {
+                        const float4 t = *reinterpret_cast<const float4 *>(ldk + 4 * q);
+                        if (4 * q + 0 < k) x[p][4 * q + 0] = fmaf(-t.x, xk, x[p][4 * q + 0]);
+                        if (4 * q + 1 < k) x[p][4 * q + 1] = fmaf(-t.y, xk, x[p][4 * q + 1]);
+                        if (4 * q + 2 < k) x[p][4 * q + 2] = fmaf(-t.z, xk, x[p][4 * q + 2]);
+                        if (4 * q + 3 < k) x[p][4 * q + 3] = fmaf(-t.w, xk, x[p][4 * q + 3]);
+                    }
                 }
             }
-            yv[0] = rhs[0];
-            yv[1] = rhs[1];
+            if (j > 0) contribute(j - 1);
         }
+        if (j == 0) break;
+        __syncthreads();
+        if (warp == j)
+            for (int jj = j - 2; jj >= 0; jj--) contribute(jj);
     }
     if (prof != nullptr) {
         __syncthreads();

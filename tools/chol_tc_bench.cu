@@ -17,7 +17,7 @@ int sm_count() { return 148; }
 using namespace lk;
 
 template <bool SWAPPED>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 3)
 bench(const float *A, const float *y, float *x, int *badout, int n_groups, long long *cycles, long long *phases)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -27,7 +27,7 @@ bench(const float *A, const float *y, float *x, int *badout, int n_groups, long 
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar, 4);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -44,7 +44,7 @@ bench(const float *A, const float *y, float *x, int *badout, int n_groups, long 
     const int r = lane & 15, h = lane >> 4;
     uint32_t par = 0;
     long long total = 0;
-    long long prof[4] = {0, 0, 0, 0};
+    long long prof[32] = {0};
     int ngr = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         float yv[2];
@@ -67,7 +67,7 @@ bench(const float *A, const float *y, float *x, int *badout, int n_groups, long 
         __syncthreads();
         tmem_fence_after();
         const long long t0 = clock64();
-        ctc::solve4<SWAPPED>(tmem_base, yv, ws, bar, par, tid, prof);
+        ctc::solve4<false, SWAPPED>(tmem_base, yv, ws, bar, par, tid, prof);  // template flag: block Gauss-Jordan
         total += clock64() - t0;
         ngr++;
         __syncthreads();
@@ -81,8 +81,11 @@ bench(const float *A, const float *y, float *x, int *badout, int n_groups, long 
     }
     if (tid == 0) {
         cycles[blockIdx.x] = ngr ? total / ngr : 0;
-        for (int i = 0; i < 4; i++) phases[blockIdx.x * 4 + i] = ngr ? prof[i] / ngr : 0;
+        for (int i = 0; i < 32; i++)
+            if (i < 4 || i >= 16) phases[blockIdx.x * 32 + i] = ngr ? prof[i] / ngr : 0;
     }
+    if (tid == 96)
+        for (int i = 4; i < 16; i++) phases[blockIdx.x * 32 + i] = ngr ? prof[i] / ngr : 0;
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
@@ -121,7 +124,10 @@ int main(int argc, char **argv)
     for (int u = 0; u < n_unique; u++) {
         const int n = 20 + (u * 37) % 400;  // rows in the Gram: rank-deficient to well-conditioned
         std::vector<float> M((size_t)n * K);
-        for (auto &v : M) v = (rand() / (float)RAND_MAX - 0.5f) * 0.3f;
+        // every fourth system is badly conditioned (large Gram, small ridge: cond ~1e4-1e5)
+        const float mscale = (u % 4 == 3) ? 1.5f : 0.3f;
+        const float ridge = (u % 4 == 3) ? 0.1f : 0.6f;
+        for (auto &v : M) v = (rand() / (float)RAND_MAX - 0.5f) * mscale;
         float *a = &A[(size_t)u * K * K];
         for (int i = 0; i < K * K; i++) a[i] = 0.f;
         for (int t = 0; t < n; t++)
@@ -129,7 +135,7 @@ int main(int argc, char **argv)
                 for (int j = 0; j < K; j++) a[i * K + j] += 40.f * M[t * K + i] * M[t * K + j];
         // OtOr-like dense SPD term + ridge
         for (int i = 0; i < K; i++)
-            for (int j = 0; j < K; j++) a[i * K + j] += 0.05f + (i == j ? 0.6f : 0.f);
+            for (int j = 0; j < K; j++) a[i * K + j] += 0.05f + (i == j ? ridge : 0.f);
         for (int i = 0; i < K; i++) y[(size_t)u * K + i] = rand() / (float)RAND_MAX * 41.f;
     }
     for (int sidx = n_unique; sidx < n_sys; sidx++) {
@@ -148,7 +154,7 @@ int main(int argc, char **argv)
     cudaMalloc(&dbad, n_sys * 4);
     cudaMalloc(&dc, 148 * 8 * 8);
     long long *dph;
-    cudaMalloc(&dph, 148 * 8 * 8 * 4);
+    cudaMalloc(&dph, 148 * 8 * 8 * 32);
     cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dy, y.data(), y.size() * 4, cudaMemcpyHostToDevice);
     const int smem = 1024 + ctc::WS_BYTES + 64;
@@ -177,7 +183,8 @@ int main(int argc, char **argv)
         cudaMemcpy(xs.data(), dx, xs.size() * 4, cudaMemcpyDeviceToHost);
         cudaMemcpy(bad.data(), dbad, n_sys * 4, cudaMemcpyDeviceToHost);
         cudaMemcpy(cyc.data(), dc, grid * 8, cudaMemcpyDeviceToHost);
-        double worst = 0, mean = 0;
+        double worst = 0, mean = 0, mean_ill = 0;
+        int n_ill = 0;
         int nbad = 0, worst_s = -1;
         for (int sidx = 0; sidx < n_sys; sidx++) {
             const double *xr = &xref[(size_t)(sidx % n_unique) * K];
@@ -189,24 +196,31 @@ int main(int argc, char **argv)
             double rel = std::sqrt(num / den);
             if (!(rel == rel)) rel = 1e30;
             mean += rel;
+            if ((sidx % n_unique) % 4 == 3) mean_ill += rel, n_ill++;
             if (rel > worst) worst = rel, worst_s = sidx;
             nbad += bad[sidx];
         }
         long long csum = 0;
         for (auto c : cyc) csum += c;
-        std::vector<long long> ph(grid * 4);
-        cudaMemcpy(ph.data(), dph, grid * 32, cudaMemcpyDeviceToHost);
-        long long phs[4] = {0, 0, 0, 0};
+        std::vector<long long> ph(grid * 32);
+        cudaMemcpy(ph.data(), dph, grid * 256, cudaMemcpyDeviceToHost);
+        long long phs[32] = {0};
         for (int b = 0; b < grid; b++)
-            for (int i = 0; i < 4; i++) phs[i] += ph[b * 4 + i];
+            for (int i = 0; i < 32; i++) phs[i] += ph[b * 32 + i];
+        printf("   warp 3 (cycles per group): wait-diag %lld  tmem-ld %lld  trsm %lld  st+tiles %lld  fence+sync %lld  mma-wait %lld | back: products+reduce %lld  sync+wait %lld\n",
+               phs[4] / grid, phs[5] / grid, phs[6] / grid, phs[7] / grid, phs[8] / grid, phs[9] / grid, phs[10] / grid, phs[11] / grid);
+        printf("   per step (thread 0): diag+wait %lld %lld %lld %lld | trsm %lld %lld %lld %lld | mma issue %lld %lld %lld\n",
+               phs[16] / grid, phs[17] / grid, phs[18] / grid, phs[19] / grid, phs[20] / grid, phs[21] / grid,
+               phs[22] / grid, phs[23] / grid, phs[24] / grid, phs[25] / grid, phs[26] / grid);
         printf("   phases per group (cycles): diag %lld  trsm+tiles %lld  mma %lld  back-subst %lld\n", phs[0] / grid,
                phs[1] / grid, phs[2] / grid, phs[3] / grid);
         // SM cycles per system: kernel time * clock / (systems per SM)
         const double per_sys_us = ms * 1e3 / n_sys * 148.0;
         printf("%-28s occ %d: %.3f ms for %d systems = %.2f us*SM per system (%.0f cycles @1.9GHz); "
-               "group latency %lld cycles; rel err worst %.3e (sys %d) mean %.3e; bad flags %d\n",
+               "group latency %lld cycles; rel err worst %.3e (sys %d) mean %.3e (badly conditioned quarter %.3e); "
+               "bad flags %d\n",
                label, occ, ms, n_sys, per_sys_us, per_sys_us * 1900.0, csum / grid, worst, worst_s,
-               mean / n_sys, nbad);
+               mean / n_sys, mean_ill / (n_ill ? n_ill : 1), nbad);
         if (worst > 1e-3) {
             const int sidx = worst_s < 0 ? 0 : worst_s;
             printf("   x[%d][0..7] gpu:", sidx);
@@ -220,6 +234,7 @@ int main(int argc, char **argv)
             printf("\n");
         }
     };
-    for (int occ = 1; occ <= 4; occ++) run(bench<false>, occ, "LBO=128 (K), SBO=512 (rows)");
+    for (int occ = 1; occ <= 3; occ++) run(bench<false>, occ, "blocked Cholesky");
+    for (int occ = 1; occ <= 3; occ++) run(bench<true>, occ, "block Gauss-Jordan");
         return 0;
 }
