@@ -1,7 +1,8 @@
 """
 GPU parity of the tensor-core ALS kernel (als_tc.cu: k = 64, bf16 gather,
 unweighted / uniformly weighted Gram) against the oracle that rounds the gathered
-rows to bf16 the same way, and against the SIMT kernel.
+rows to bf16 the same way, and against the SIMT kernel — for every solve variant
+the library can be switched to.
 """
 
 import numpy as np
@@ -14,6 +15,22 @@ from lkpy_b200 import _lib, data, engine
 from helpers import rel_fro, small_synth
 
 pytestmark = pytest.mark.gpu
+
+# solve variants of the tensor-core kernel (environment switches read by launch_als_tc / dispatch)
+VARIANTS = {
+    "tc-cholesky": {},  # default: blocked Cholesky with tcgen05 trailing updates (chol_tc.cuh)
+    "tc-gauss-jordan": {"LK_ALS_GJ": "1"},  # block Gauss-Jordan variant of the same
+    "smem-solve": {"LK_ALS_TCS": "0"},  # systems drained to shared memory, one warp per solve
+    "smem-solve-wide": {"LK_ALS_TCS": "0", "LK_ALS_TC_INTERLEAVE": "0"},  # one accumulator per 64 columns
+    "register-solve": {"LK_ALS_TC": "2"},  # als_tcr.cu experiment
+}
+
+
+def _set(monkeypatch, variant):
+    for key in ("LK_ALS_TC", "LK_ALS_TCS", "LK_ALS_GJ", "LK_ALS_TC_INTERLEAVE"):
+        monkeypatch.delenv(key, raising=False)
+    for key, val in VARIANTS[variant].items():
+        monkeypatch.setenv(key, val)
 
 
 def _run(mode, csr, this, other, reg, chunk_nnz=engine.DEFAULT_CHUNK_NNZ):
@@ -40,12 +57,10 @@ def _oracle(mode, csr, this, other, reg):
     return oracle.als_half_f64(mode, csr, this, other, otor_mat=o64, reg=reg, bf16_other=True)
 
 
-# generation "2" = als_tcr.cu (register-resident solve, the default), "1" = als_tc.cu
-@pytest.mark.parametrize("gen,interleave", [("2", "1"), ("1", "1"), ("1", "0")])
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("mode", ["implicit", "explicit"])
-def test_tc_kernel_parity(cuda_lib, monkeypatch, mode, gen, interleave):
-    monkeypatch.setenv("LK_ALS_TC", gen)
-    monkeypatch.setenv("LK_ALS_TC_INTERLEAVE", interleave)
+def test_tc_kernel_parity(cuda_lib, monkeypatch, mode, variant):
+    _set(monkeypatch, variant)
     inter = small_synth(900, 500, 40000, seed=21)
     rng = np.random.default_rng(21)
     k = 64
@@ -60,38 +75,76 @@ def test_tc_kernel_parity(cuda_lib, monkeypatch, mode, gen, interleave):
         got, delta, plan = _run(mode, csr, this, other, 0.1)
         assert plan.vals_uniform == (mode == "implicit")
         ref, dref = _oracle(mode, csr, this, other, 0.1)
-        assert rel_fro(got, ref) < 1e-4, rel_fro(got, ref)
+        assert rel_fro(got, ref) < 1e-4, rel_fro(got, ref)  # north_star tolerance
         assert delta == pytest.approx(dref, rel=1e-3)
         empty = np.diff(csr.indptr) == 0
         assert np.all(got[empty] == 0.0)
         # the SIMT kernel on the same inputs agrees to rounding
         monkeypatch.setenv("LK_ALS_TC", "0")
         simt, _, _ = _run(mode, csr, this, other, 0.1)
-        monkeypatch.setenv("LK_ALS_TC", gen)
+        _set(monkeypatch, variant)
         assert rel_fro(got, simt) < 2e-5
 
 
-@pytest.mark.parametrize("gen", ["2", "1"])
-def test_tc_split_rows_deterministic(cuda_lib, monkeypatch, gen):
-    monkeypatch.setenv("LK_ALS_TC", gen)
+@pytest.mark.parametrize("variant", ["tc-cholesky", "tc-gauss-jordan", "smem-solve", "register-solve"])
+@pytest.mark.parametrize("mode", ["implicit", "explicit"])
+def test_tc_split_rows_deterministic(cuda_lib, monkeypatch, variant, mode):
+    _set(monkeypatch, variant)
     inter = small_synth(300, 200, 20000, seed=5)
-    _ui, iu = data.als_implicit_matrices(inter, 40.0)
     rng = np.random.default_rng(5)
+    if mode == "implicit":
+        _ui, iu = data.als_implicit_matrices(inter, 40.0)
+    else:
+        coo = inter.coo(rng.standard_normal(inter.nnz).astype(np.float32))
+        iu = data.InteractionCSR.from_scipy(coo.T)
     p = (rng.standard_normal((300, 64)) * 0.1).astype(np.float32)
     q = (rng.standard_normal((200, 64)) * 0.1).astype(np.float32)
-    a, _, plan = _run("implicit", iu, q, p, 0.1, chunk_nnz=32)
+    a, _, plan = _run(mode, iu, q, p, 0.1, chunk_nnz=32)
     assert plan.n_split_rows > 0
-    b, _, _ = _run("implicit", iu, q, p, 0.1, chunk_nnz=32)
-    assert np.array_equal(a.view(np.int32), b.view(np.int32))
-    ref, _ = _oracle("implicit", iu, q, p, 0.1)
+    b, _, _ = _run(mode, iu, q, p, 0.1, chunk_nnz=32)
+    assert np.array_equal(a.view(np.int32), b.view(np.int32))  # bit-reproducible
+    ref, _ = _oracle(mode, iu, q, p, 0.1)
     assert rel_fro(a, ref) < 1e-4
-    c, _, _ = _run("implicit", iu, q, p, 0.1, chunk_nnz=1 << 20)
+    c, _, _ = _run(mode, iu, q, p, 0.1, chunk_nnz=1 << 20)
     assert rel_fro(a, c) < 1e-5
+
+
+@pytest.mark.parametrize("variant", ["tc-cholesky", "tc-gauss-jordan"])
+def test_tc_solve_badly_conditioned(cuda_lib, monkeypatch, variant):
+    """Large Gram, small ridge (cond ~1e4): the tensor-core solve stays within a small factor of what
+    f32 arithmetic can deliver (the f32 oracle's own distance to the f64 oracle)."""
+    _set(monkeypatch, variant)
+    inter = small_synth(400, 300, 60000, seed=9)
+    ui, _ = data.als_implicit_matrices(inter, 40.0)
+    rng = np.random.default_rng(9)
+    p = (rng.standard_normal((400, 64)) * 0.1).astype(np.float32)
+    q = rng.standard_normal((300, 64)).astype(np.float32)  # trained-scale-and-beyond item factors
+    reg = 0.01
+    got, _, _ = _run("implicit", ui, p, q, reg)
+    ref, _ = _oracle("implicit", ui, p, q, reg)
+    o32, _ = oracle.otor(oracle.bf16_round(q), reg)
+    cpu32, _ = oracle.als_half("implicit", ui, p, q, otor_mat=o32, bf16_other=True)
+    e_gpu, e_cpu = rel_fro(got, ref), rel_fro(cpu32, ref)
+    assert e_gpu < max(1e-4, 3.0 * e_cpu), (e_gpu, e_cpu)
+
+
+def test_tc_zero_weight_falls_back(cuda_lib, monkeypatch):
+    """weight = 0 makes every confidence 0: (A / v) is undefined, the shared-memory solve takes over."""
+    _set(monkeypatch, "tc-cholesky")
+    inter = small_synth(200, 150, 5000, seed=3)
+    ui, _ = data.als_implicit_matrices(inter, 0.0)
+    rng = np.random.default_rng(3)
+    p = (rng.standard_normal((200, 64)) * 0.1).astype(np.float32)
+    q = (rng.standard_normal((150, 64)) * 0.1).astype(np.float32)
+    got, _, _ = _run("implicit", ui, p, q, 0.1)
+    ref, _ = _oracle("implicit", ui, p, q, 0.1)
+    assert np.isfinite(got).all()
+    assert rel_fro(got, ref) < 1e-4
 
 
 def test_tc_non_uniform_weights_fall_back(cuda_lib, monkeypatch):
     """use_ratings=True confidences are not uniform: the SIMT kernel must take the launch."""
-    monkeypatch.setenv("LK_ALS_TC", "2")
+    _set(monkeypatch, "tc-cholesky")
     inter = small_synth(400, 300, 15000, seed=8)
     ui, _ = data.als_implicit_matrices(inter, 40.0, use_ratings=True)
     rng = np.random.default_rng(8)
