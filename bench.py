@@ -293,10 +293,25 @@ def run_reference(args, rank: int) -> None:
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }  # fmt: skip
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else (NCCL's version banner, library
+    chatter written to fd 1) was redirected to stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main() -> None:
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -434,10 +449,23 @@ def main() -> None:
             wall = (time.perf_counter() - t0) * 1e3 / args.steps
             e2e_ms = e0.elapsed_time(e1) / args.steps
             nbytes = (hp.numel() + hq.numel()) * 4
+            h2d, d2h = nbytes, nbytes + 16
+            api = "ImplicitMFTrainer.train_epoch_e2e: H2D factor tables, epoch, D2H factor tables + deltas; CSR resident"
+            if world > 1:
+                import torch.distributed as dist
+
+                # every rank uploads the rows it owns, rank 0 reads the whole model back: sum over ranks
+                t = torch.tensor([tr.e2e_bytes[0], tr.e2e_bytes[1], max(e2e_ms, wall)], device=dev, dtype=torch.float64)
+                tmax = t.clone()
+                dist.all_reduce(t)
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                h2d, d2h = int(t[0].item()), int(t[1].item())
+                e2e_ms = wall = float(tmax[2].item())
+                api = ("ShardedImplicitMFTrainer.train_epoch_e2e: each rank uploads its row shards, NVLink all-gather, "
+                       "epoch, rank 0 reads the whole model back (others their shards); bytes summed over ranks")
             results["e2e"] = {
-                "value": max(e2e_ms, wall), "unit": UNIT, "h2d_bytes_per_step": nbytes,
-                "d2h_bytes_per_step": nbytes + 16,
-                "api": "ImplicitMFTrainer.train_epoch_e2e: H2D factor tables, epoch, D2H factor tables + deltas; CSR resident",
+                "value": max(e2e_ms, wall), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "api": api,
             }  # fmt: skip
             log(f"[bench] ALS e2e: {results['e2e']['value']:.3f} ms/epoch")
         del tr, scorer
@@ -487,7 +515,7 @@ def main() -> None:
                          if "fp32" in results else None),
             "knn": knn,
         }  # fmt: skip
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 

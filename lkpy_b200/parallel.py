@@ -163,6 +163,38 @@ class ShardedImplicitMFTrainer(ImplicitMFTrainer):
         self.epochs_trained += 1
         return du, di
 
+    def train_epoch_e2e(self, host_users: torch.Tensor, host_items: torch.Tensor) -> dict[str, float]:
+        """
+        The host-array epoch of ``ALSTrainerBase.train_epoch_e2e`` for the sharded trainer: every rank
+        uploads only the rows it owns (the PCIe links work in parallel), the replicas are completed
+        over NVLink, and after the epoch rank 0 reads the whole model back while the other ranks
+        refresh only their own rows.  ``e2e_bytes`` holds this rank's (h2d, d2h) byte counts.
+        """
+        ulo, uhi = self.u_slice
+        ilo, ihi = self.i_slice
+        self.d_users[ulo:uhi].copy_(host_users[ulo:uhi], non_blocking=True)
+        self.d_items[ilo:ihi].copy_(host_items[ilo:ihi], non_blocking=True)
+        allgather_rows(self.d_users, self.u_bounds, self.rank, self.world, self.group)
+        allgather_rows(self.d_items, self.i_bounds, self.rank, self.world, self.group)
+        du, di = self.train_epoch_device()
+        if self.user_peers is None:
+            d = torch.cat([du, di])
+            dist.all_reduce(d, group=self.group)
+        else:
+            d = torch.cat([du, di])  # already reduced (the all-reduce is the exchange barrier)
+        k4 = self.d_users.shape[1] * 4
+        if self.rank == 0:
+            host_users.copy_(self.d_users, non_blocking=True)
+            host_items.copy_(self.d_items, non_blocking=True)
+            d2h = (self.d_users.shape[0] + self.d_items.shape[0]) * k4
+        else:
+            host_users[ulo:uhi].copy_(self.d_users[ulo:uhi], non_blocking=True)
+            host_items[ilo:ihi].copy_(self.d_items[ilo:ihi], non_blocking=True)
+            d2h = ((uhi - ulo) + (ihi - ilo)) * k4
+        self.e2e_bytes = (((uhi - ulo) + (ihi - ilo)) * k4, d2h + 16)
+        deltas = d.cpu()  # device->host read of the step's result; synchronises
+        return {"deltaP": float(np.sqrt(deltas[0])), "deltaQ": float(np.sqrt(deltas[1]))}
+
     def train_epoch(self):
         du, di = self.train_epoch_device()
         d = torch.cat([du, di])
