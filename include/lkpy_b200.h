@@ -227,6 +227,25 @@ typedef struct lk_knn_score_args {
 LK_API int64_t lk_knn_score_warps(void);
 LK_API int lk_knn_score_batch(const lk_knn_score_args *args, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Batched top-N (the step after the scorer)
+ *
+ * Replaces `_accel.data.argtopn` (src/accel/data/sorting.rs:131-170; the selection
+ * behind ItemList.top_n, src/lenskit/data/_items.py:942-998, and TopNRanker,
+ * src/lenskit/basic/topn.py:32-69) for every column of a row-major score matrix
+ * d_scores[n_rows][ld] (rows = items, columns = score vectors, e.g. Q . X^T).
+ * Column c gets the indices of its n largest non-NaN scores in the reference's
+ * order — the kernel replays the reference's indirect min-heap
+ * (src/accel/indirect/heap.rs), so ties are cut and ordered exactly as there:
+ *   d_out_idx[c*n + t]  item index of rank t, -1 beyond the column's count
+ *   d_out_val[c*n + t]  its score (NaN beyond the count); may be NULL
+ *   d_out_cnt[c]        min(n, number of non-NaN scores in the column)
+ * n in 1..lk_topn_max(); n_rows < 2^31.
+ * ---------------------------------------------------------------------- */
+LK_API int lk_topn_max(void);
+LK_API int lk_topn_columns(const float *d_scores, int64_t n_rows, int64_t n_cols, int64_t ld, int32_t n,
+                           int32_t *d_out_idx, float *d_out_val, int32_t *d_out_cnt, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

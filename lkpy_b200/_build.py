@@ -16,7 +16,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "liblkpy_b200.so"
-SOURCES = ["capi.cu", "als_kernels.cu", "als_tc.cu", "als_tcr.cu", "knn_build.cu", "knn_score.cu"]
+SOURCES = ["capi.cu", "als_kernels.cu", "als_tc.cu", "als_tcr.cu", "knn_build.cu", "knn_score.cu", "topn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
@@ -35,7 +35,9 @@ def _stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", CSRC / "als_common.cuh", CSRC / "tc_common.cuh"]
+    deps = [CSRC / s for s in SOURCES] + [
+        CSRC / "common.cuh", CSRC / "als_common.cuh", CSRC / "tc_common.cuh", CSRC / "chol_tc.cuh",
+    ]  # fmt: skip
     deps.append(CSRC.parent.parent / "include" / "lkpy_b200.h")
     return any(d.stat().st_mtime > t for d in deps)
 

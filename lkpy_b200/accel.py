@@ -279,7 +279,34 @@ def score_implicit(sims, ref_items, tgt_items, max_nbrs: int, min_nbrs: int):
     return _score(sims, ref_items, None, tgt_items, max_nbrs, min_nbrs)
 
 
+def argtopn(scores: Any, n: int) -> np.ndarray:
+    """
+    ``_accel.data.argtopn`` (src/accel/data/sorting.rs:131-170): indices of the ``n`` largest non-NaN
+    (and non-null) scores, in the reference's order.  One vector is one thread's work for
+    ``lk_topn_columns`` — this entry point exists for interface parity; batches go through
+    ``argtopn_batch`` / ``ALSBase.recommend_batch``.
+    """
+    s = _to_f32(scores)
+    return argtopn_batch(s[None, :], n)[0]
+
+
+def argtopn_batch(scores: Any, n: int) -> list[np.ndarray]:
+    """``argtopn`` for every row of a host matrix ``scores`` [n_vectors, n_items] in one launch."""
+    dev = _lib.require_device()
+    s = np.ascontiguousarray(scores, dtype=np.float32)
+    if s.ndim != 2:
+        raise TypeError("scores must be 2-dimensional")
+    n = int(min(n, s.shape[1]))
+    if n <= 0 or s.shape[0] == 0:
+        return [np.empty(0, dtype=np.int32) for _ in range(s.shape[0])]
+    d = torch.from_numpy(s).to(dev).T.contiguous()  # item-major: the kernel scans a column per thread
+    idx, _val, cnt = engine.topn_columns(d, n, with_values=False)
+    idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+    return [idx[b, : cnt[b]].copy() for b in range(s.shape[0])]
+
+
 #: ``from lkpy_b200.accel import als, knn`` mirrors ``from lenskit._accel import als, knn``
+data = SimpleNamespace(argtopn=argtopn, argtopn_batch=argtopn_batch)
 als = SimpleNamespace(
     train_implicit_matrix=train_implicit_matrix, train_explicit_matrix=train_explicit_matrix
 )

@@ -105,6 +105,97 @@ class ALSBase(UsesTrainer, Component):
         scores[mask] = self.item_embeddings[item_nums[mask], :] @ u_feat
         return self.finalize_scores(user_num, ItemList(items, scores=scores), u_offset)
 
+    # ------------------------------------------------------------------------------------------
+    # Batched inference on the device (SURVEY.md §8f N1 + N2): what the reference does one query at
+    # a time — ALSBase.__call__ (als/_common.py:133-175), fold-in (_implicit.py:77-130), TopNRanker
+    # → ItemList.top_n → argtopn (basic/topn.py:32-69, data/_items.py:942-998,
+    # src/accel/data/sorting.rs:131-170) — for a whole batch of queries with the factors resident
+    # in HBM: fold-in rows by the training kernel, scores by one library GEMM (Q · Xᵀ, item-major so
+    # the selection kernel's scan is coalesced), top-N by lk_topn_columns.
+    # ------------------------------------------------------------------------------------------
+
+    def _device_items(self) -> torch.Tensor:
+        dev = _lib.require_device()
+        cached = self.__dict__.get("_d_items_cache")
+        if cached is None or cached[0] is not self.item_embeddings:
+            t = torch.from_numpy(np.ascontiguousarray(self.item_embeddings, dtype=np.float32)).to(dev)
+            self.__dict__["_d_items_cache"] = cached = (self.item_embeddings, t)
+        return cached[1]
+
+    def fold_in_batch(self, histories: list[ItemList]) -> torch.Tensor:  # pragma: no cover
+        raise NotImplementedError
+
+    def batch_offsets(self, user_nums: np.ndarray, fold_bias: np.ndarray | None):
+        """(per-item offset [n_items] or None, per-query offset [B] or None) added to Q · Xᵀ."""
+        return None, None
+
+    def embed_batch(self, queries) -> tuple[torch.Tensor, np.ndarray, np.ndarray, np.ndarray | None]:
+        """
+        Query embeddings on the device: ``(X [B, k], scorable [B] bool, user_nums [B] (-1 unknown),
+        fold-in user offsets or None)`` with the precedence rules of ``__call__``.
+        """
+        dev = _lib.require_device()
+        queries = [RecQuery.create(q) for q in queries]
+        k = self.item_embeddings.shape[1]
+        B = len(queries)
+        user_nums = np.full(B, -1, dtype=np.int64)
+        for b, q in enumerate(queries):
+            if q.user_id is not None and self.users is not None:
+                num = self.users.number(q.user_id, missing=None)
+                if num is not None:
+                    user_nums[b] = num
+        fold = np.array(
+            [q.query_items is not None and len(q.query_items) > 0 and self.config.user_embeddings != "prefer"
+             for q in queries], dtype=bool,
+        )  # fmt: skip
+        X = torch.zeros((B, k), dtype=torch.float32, device=dev)
+        scorable = fold.copy()
+        fold_bias = None
+        if fold.any():
+            rows = np.flatnonzero(fold)
+            emb, fold_bias_rows = self.fold_in_batch([queries[b].query_items for b in rows])
+            X[torch.from_numpy(rows).to(dev)] = emb
+            if fold_bias_rows is not None:
+                fold_bias = np.full(B, np.nan, dtype=np.float32)
+                fold_bias[rows] = fold_bias_rows
+        known = ~fold & (user_nums >= 0) & (self.user_embeddings is not None)
+        if known.any():
+            rows = np.flatnonzero(known)
+            emb = torch.from_numpy(np.ascontiguousarray(self.user_embeddings[user_nums[rows]], dtype=np.float32))
+            X[torch.from_numpy(rows).to(dev)] = emb.to(dev)
+            scorable |= known
+        return X, scorable, user_nums, fold_bias
+
+    def score_matrix(self, queries) -> torch.Tensor:
+        """Scores of every item for every query, item-major: [n_items, B] f32, NaN columns for unscorable queries."""
+        X, scorable, user_nums, fold_bias = self.embed_batch(queries)
+        S = self._device_items() @ X.T  # [n_items, B]; fp32 GEMM (allow_tf32 is off by default)
+        item_off, query_off = self.batch_offsets(user_nums, fold_bias)
+        if item_off is not None:
+            S += torch.from_numpy(item_off.astype(np.float32)).to(S.device)[:, None]
+        if query_off is not None:
+            S += torch.from_numpy(query_off.astype(np.float32)).to(S.device)[None, :]
+        if not scorable.all():
+            S[:, torch.from_numpy(np.flatnonzero(~scorable)).to(S.device)] = float("nan")
+        return S
+
+    def recommend_batch(self, queries, n: int) -> list[ItemList]:
+        """Top-``n`` items for every query: the batched form of scorer → ``TopNRanker``."""
+        S = self.score_matrix(queries)
+        n_eff = min(int(n), S.shape[0])
+        if n_eff <= 0:
+            return [ItemList([], scores=np.empty(0, dtype=np.float32)) for _ in range(S.shape[1])]
+        idx, val, cnt = engine.topn_columns(S, n_eff)
+        idx, val, cnt = idx.cpu().numpy(), val.cpu().numpy(), cnt.cpu().numpy()
+        out = []
+        for b in range(S.shape[1]):
+            c = int(cnt[b])
+            out.append(
+                ItemList(item_ids=self.items.ids(idx[b, :c]), item_nums=idx[b, :c].copy(), vocabulary=self.items,
+                         scores=val[b, :c].copy())
+            )  # fmt: skip
+        return out
+
 
 def _solve_cholesky(A: np.ndarray, y: np.ndarray) -> np.ndarray:
     """``lenskit.math.solve.solve_cholesky`` (math/solve.py:17-41); host fold-in only."""
@@ -266,6 +357,49 @@ class ImplicitMFScorer(ALSBase):
         y = M.T @ (val + 1.0)
         return _solve_cholesky(A, y.astype(A.dtype)), None
 
+    def fold_in_batch(self, histories: list[ItemList]):
+        """
+        ``new_user_embedding`` for a batch of histories on the device: the histories become the rows
+        of a CSR matrix and one ``lk_als_half_epoch`` (the training kernel, fp32 item table) solves
+        them all — same math as ``_train_new_row`` (``_implicit.py:109-130``).
+        """
+        dev = _lib.require_device()
+        k = self.item_embeddings.shape[1]
+        cols, vals, indptr = [], [], [0]
+        for h in histories:
+            ri = h.numbers(vocabulary=self.items, missing="negative")
+            good = ri >= 0
+            if self.config.use_ratings:
+                ratings = h.field("rating")
+                if ratings is None:
+                    raise ValueError("no ratings in user items")
+                v = np.asarray(ratings)[good] * self.config.weight
+            else:
+                v = np.full(int(good.sum()), self.config.weight)
+            c = ri[good].astype(np.int32)
+            order = np.argsort(c, kind="stable")  # the CSR container wants ascending columns
+            cols.append(c[order])
+            vals.append(np.asarray(v, dtype=np.float32)[order])
+            indptr.append(indptr[-1] + len(c))
+        csr = InteractionCSR(
+            np.asarray(indptr, dtype=np.int32),
+            np.concatenate(cols) if cols else np.empty(0, np.int32),
+            np.concatenate(vals) if vals else np.empty(0, np.float32),
+            (len(histories), self.item_embeddings.shape[0]),
+        )
+        dm = engine.DeviceCSR.from_host(csr, dev)
+        plan = engine.ALSHalfPlan.create(dm, k)
+        d_items = self._device_items()
+        ws = engine.OtorWorkspace.create(k, dev)
+        otor = engine.als_otor(d_items, float(self.config.user_reg), ws, None)
+        x = torch.zeros((len(histories), k), dtype=torch.float32, device=dev)
+        plan.sqdelta.zero_()
+        plan.status.zero_()
+        engine.als_half_epoch(plan, _lib.LK_ALS_IMPLICIT, x, d_items, otor=otor)
+        if int(plan.status.item()):
+            raise RuntimeError("ALS solve error: a fold-in system is not positive definite")
+        return x, None
+
 
 class ImplicitMFTrainer(ALSTrainerBase):
     MODE = _lib.LK_ALS_IMPLICIT
@@ -372,6 +506,23 @@ class BiasedMFScorer(ALSBase):
         biases = np.full(len(items), self.bias.global_bias + user_bias, dtype=np.float32)
         biases[inums >= 0] += self.bias.item_biases[inums[inums >= 0]]
         return ItemList(items, scores=scores + biases)
+
+    def fold_in_batch(self, histories: list[ItemList]):
+        """Explicit fold-in keeps the reference's host path per query (``_explicit.py:121-147``)."""
+        dev = _lib.require_device()
+        embs, offs = [], []
+        for h in histories:
+            e, off = self.new_user_embedding(None, h)
+            embs.append(np.asarray(e, dtype=np.float32))
+            offs.append(off)
+        return torch.from_numpy(np.stack(embs)).to(dev), np.asarray(offs, dtype=np.float32)
+
+    def batch_offsets(self, user_nums: np.ndarray, fold_bias: np.ndarray | None):
+        """``finalize_scores`` for a batch: global + item bias per item, user bias per query."""
+        ub = np.where(user_nums >= 0, self.bias.user_biases[np.maximum(user_nums, 0)], 0.0).astype(np.float32)
+        if fold_bias is not None:
+            ub = np.where(np.isnan(fold_bias), ub, fold_bias).astype(np.float32)
+        return (self.bias.item_biases + self.bias.global_bias).astype(np.float32), ub
 
 
 class BiasedMFTrainer(ALSTrainerBase):

@@ -435,3 +435,35 @@ class KnnScorerState:
         if int(self.status.item()) == 2:
             raise ValueError("similarity is null")
         return scores[:nt], counts[:nt]
+
+
+# ---------------------------------------------------------------------------
+# batched top-N
+# ---------------------------------------------------------------------------
+
+
+def topn_columns(scores: torch.Tensor, n: int, with_values: bool = True):
+    """
+    Top-``n`` of every column of ``scores`` [n_items, n_vectors] (f32, unit column stride) with
+    the reference's ``argtopn`` semantics (``lk_topn_columns``): returns
+    ``(idx [n_vectors, n] int32 with -1 padding, val [n_vectors, n] f32 or None, cnt [n_vectors] int32)``.
+    """
+    _lib.require_device()
+    if scores.dtype != torch.float32 or scores.dim() != 2 or (scores.shape[1] > 1 and scores.stride(1) != 1):
+        raise TypeError("scores must be a 2-D float32 tensor with contiguous columns")
+    n_rows, n_cols = scores.shape
+    n = int(n)
+    if not 1 <= n <= int(lib().lk_topn_max()):
+        raise ValueError(f"n must be in 1..{int(lib().lk_topn_max())}")
+    dev = scores.device
+    idx = torch.empty((n_cols, n), dtype=torch.int32, device=dev)
+    val = torch.empty((n_cols, n), dtype=torch.float32, device=dev) if with_values else None
+    cnt = torch.empty((max(n_cols, 1),), dtype=torch.int32, device=dev)
+    check(
+        lib().lk_topn_columns(
+            ptr(scores), n_rows, n_cols, scores.stride(0) if n_rows > 1 else max(n_cols, 1), n,
+            ptr(idx), ptr(val), ptr(cnt), stream_ptr(),
+        ),
+        "lk_topn_columns",
+    )  # fmt: skip
+    return idx, val, cnt[:n_cols]

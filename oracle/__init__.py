@@ -80,6 +80,8 @@ def lib():
             C.c_int, C.c_int, _f32p, _i32p,
         ]  # fmt: skip
         L.lk_oracle_knn_score.restype = C.c_int
+        L.lk_oracle_argtopn_f32.argtypes = [_f32p, C.c_int64, C.c_int64, _i32p]
+        L.lk_oracle_argtopn_f32.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -330,3 +332,17 @@ def knn_score(
     if rc:
         raise IndexError("item index out of range")
     return scores, counts
+
+
+def argtopn(scores: np.ndarray, n: int) -> np.ndarray:
+    """
+    ``lenskit._accel.data.argtopn`` (``src/accel/data/sorting.rs:131-170``): indices of the ``n``
+    largest non-NaN scores in descending score order, selected and ordered by the reference's
+    indirect min-heap (``src/accel/indirect/heap.rs``) — including which of several equal scores
+    survive at the cut and the order equal scores come out in.
+    """
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    n = int(min(max(n, 0), len(scores)))
+    out = np.empty(max(n, 1), dtype=np.int32)
+    cnt = lib().lk_oracle_argtopn_f32(scores, len(scores), n, out)
+    return out[:cnt].copy()
