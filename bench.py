@@ -468,6 +468,8 @@ def main() -> None:
                 "d2h_bytes_per_step": d2h, "api": api,
             }  # fmt: skip
             log(f"[bench] ALS e2e: {results['e2e']['value']:.3f} ms/epoch")
+            if rank == 0 and world == 1 and not args.no_knn:
+                results["recommend"] = bench_recommend(args, tr, dev, peak, peak_src)
         del tr, scorer
         torch.cuda.empty_cache()
 
@@ -514,12 +516,80 @@ def main() -> None:
             "als_fp32": ({"ms_per_epoch": results["fp32"]["ms_per_epoch"], "roofline": results["fp32"]["roofline"]}
                          if "fp32" in results else None),
             "knn": knn,
+            "recommend": results.get("recommend"),
         }  # fmt: skip
         emit(line)
     if world > 1:
         import torch.distributed as dist
 
         dist.destroy_process_group()
+
+
+def bench_recommend(args, tr, dev, peak, peak_src) -> dict:
+    """
+    SURVEY.md §8f N1/N2: top-100 of all items for a batch of users from the factors just trained —
+    one fp32 library GEMM (Q · Xᵀ, item-major) + lk_topn_columns (the reference's heap, one thread
+    per user).  CPU figure: the reference's per-query path (f32 matvec + argtopn), one thread.
+    """
+    import torch
+
+    from lkpy_b200 import engine
+
+    n_top, batch = 100, min(131072, int(tr.d_users.shape[0]))  # one thread per user: large batches fill the GPU
+    q, p = tr.d_items, tr.d_users
+    rng = np.random.default_rng(11)
+    users = torch.from_numpy(np.sort(rng.choice(p.shape[0], batch, replace=False))).to(dev)
+    x = p[users].contiguous()
+    s = q @ x.T
+    engine.topn_columns(s, n_top)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    reps = 3
+    t_gemm = t_top = 0.0
+    for _ in range(reps):
+        ev[0].record()
+        s = q @ x.T
+        ev[1].record()
+        idx, val, cnt = engine.topn_columns(s, n_top)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_gemm += ev[0].elapsed_time(ev[1]) / reps
+        t_top += ev[1].elapsed_time(ev[2]) / reps
+    n_items = q.shape[0]
+    alg = float(n_items) * batch * 4  # the selection reads every score once
+    achieved = alg / (t_top * 1e-3) / 1e9
+    out = {
+        "workload": f"top-{n_top} of {n_items} items for {batch} trained users (ML-25M-shaped ImplicitMF k={K})",
+        "users_per_s": batch / ((t_gemm + t_top) * 1e-3), "gemm_ms": t_gemm, "topn_ms": t_top,
+        "roofline": {"bound": "hbm", "kernel": "topn_columns_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes": alg,
+                     "peak_source": peak_src},
+    }  # fmt: skip
+    log(f"[bench] recommend: {batch} users x top-{n_top}: GEMM {t_gemm:.1f} ms + top-N {t_top:.1f} ms = "
+        f"{out['users_per_s']:.0f} users/s; top-N {achieved:.0f} GB/s = {achieved / peak:.3f} of peak")
+    if not args.no_cpu:
+        import oracle
+
+        qh, ph = q.cpu().numpy(), x[:256].cpu().numpy()
+        t0 = time.perf_counter()
+        done = 0
+        for u in range(len(ph)):
+            sc = qh @ ph[u]
+            oracle.argtopn(sc, n_top)
+            done += 1
+            if time.perf_counter() - t0 > 4.0:
+                break
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": done / dt, "unit": "users/s", "cores": 1, "kind": "port",
+                               "sample": f"{done} users, f32 matvec + heap argtopn each, one thread"}  # fmt: skip
+        # selection parity on the way: the device lists of the first users against the oracle on the device scores
+        sh = s[:, :8].cpu().numpy()
+        ih = idx[:8].cpu().numpy()
+        for c in range(8):
+            assert np.array_equal(ih[c], oracle.argtopn(sh[:, c], n_top)), "top-N mismatch vs oracle"
+        log(f"[bench] CPU recommend: {out['cpu_baseline']['value']:.0f} users/s (one thread)")
+    del s
+    return out
 
 
 def bench_knn(args, inter, dev, peak, peak_src, rank: int = 0, world: int = 1) -> dict | None:
