@@ -13,6 +13,7 @@
  *   POSV::solve (LAPACK sposv)                    src/accel/als/solve.rs:65-106     in-kernel Cholesky
  *   _accel.knn.compute_similarities               src/accel/knn/item_train.rs:32-93 lk_knn_geometry + lk_knn_build
  *   _accel.knn.score_explicit / score_implicit    src/accel/knn/item_score.rs:22-111 lk_knn_score_batch
+ *   _accel.data.argtopn ("next")    src/accel/data/sorting.rs:131-170 lk_topn_columns
  *
  * Conventions
  *   - plain C: pointers and sizes only; no C++/torch types cross this boundary;
