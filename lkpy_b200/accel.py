@@ -16,7 +16,6 @@ per matrix object so that the ten half-epochs of a training run upload it once.
 from __future__ import annotations
 
 import threading
-import weakref
 from types import SimpleNamespace
 from typing import Any, Callable, Generic, TypeVar
 
@@ -114,14 +113,10 @@ def as_host_csr(m: Any) -> InteractionCSR:
     raise TypeError(f"cannot interpret {type(m).__name__} as a CSR matrix")  # csr.rs:160-195
 
 
-_dev_cache: "weakref.WeakValueDictionary[int, Any]" = weakref.WeakValueDictionary()
-_cache_keep: dict[int, tuple[Any, Any]] = {}
+# device copies and plans of the host matrices the caller keeps passing in (one per epoch half):
+# keyed by object identity, a few entries, oldest evicted first
+_cache_keep: dict[tuple[int, str], tuple[Any, Any]] = {}
 _CACHE_LIMIT = 8
-
-
-class _Cached:
-    def __init__(self, **kw):
-        self.__dict__.update(kw)
 
 
 def _cached(obj: Any, tag: str, make: Callable[[], Any]) -> Any:

@@ -21,18 +21,24 @@
 // rounds the gathered rows to bf16 the same way.
 //
 // CTA = 4 warps working in lock-step groups of 4 row-chunks:
-//   phase 1  each warp gathers its own chunk through a 4-stage cp.async ring,
-//            lane 0 issues the MMAs into the warp's TMEM accumulator and commits
-//            them to mbarriers (stage free / accumulator full); the right-hand
-//            side y is accumulated on the SIMT side from the same tile;
-//   phase 2  all four warps drain the accumulators (a warp can only read its own
-//            quarter of the TMEM lanes: for M=64 rows 16w..16w+15 of *every*
-//            accumulator) into the per-warp shared-memory systems, adding OtOr or
-//            reg*n*I; chunks of split rows go to their partial slot instead and
-//            the last part to arrive reduces the slots in order (deterministic);
-//   phase 3  each warp factors and solves its own 64x64 system (als_common.cuh).
-// Two M=64 accumulators share 64 TMEM columns (lanes 0-15 / 16-31 of every
-// quarter, the "interleaved" allocation), so a CTA needs 128 columns.
+//   phase 1  each warp gathers its own chunk through a 4-stage cp.async ring, one
+//            elected lane issues the MMAs into the warp's TMEM accumulator and
+//            commits them to mbarriers (stage free / accumulator full); with uniform
+//            weights the right-hand side is a second, 8-column MMA against a ones
+//            tile, otherwise it is accumulated on the SIMT side from the same tile;
+//   phase 2  (TCS, default) the systems stay in TMEM: in implicit mode the
+//            accumulators were preloaded with OtOr / v before the group started, so
+//            unsplit rows need nothing; explicit mode adds reg*n to the diagonal in
+//            place.  Chunks of split rows write their accumulator to a partial slot
+//            and the last part to arrive sums the slots in order (deterministic);
+//   phase 3  (TCS) blocked Cholesky of the four systems with the trailing updates
+//            on the tensor cores (chol_tc.cuh), write-back by the row-owner lanes.
+//   Without TCS (LK_ALS_TCS=0) phase 2 drains the accumulators into per-warp
+//   shared-memory systems and phase 3 is one chol_solve per warp (als_common.cuh).
+// A warp can only read its own quarter of the TMEM lanes: for M=64, rows
+// 16w..16w+15 of *every* accumulator.  Two M=64 accumulators share 64 TMEM columns
+// (lanes 0-15 / 16-31 of every quarter, the "interleaved" allocation), so a CTA
+// needs 128 columns (+32 for the right-hand sides).
 
 #include "chol_tc.cuh"
 

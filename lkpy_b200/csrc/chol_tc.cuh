@@ -17,12 +17,17 @@
 //      into the dead panel columns of TMEM (the back substitution reads it there)
 //      and write X as two tf32 K-major operand tiles: hi = X with the low 13
 //      mantissa bits cleared, lo = X - hi (exact in f32);
-//   3. one thread issues, per system, D[:, 16(j+1):] -= X X^T as three
-//      tcgen05.mma.kind::tf32 (hi.hi + hi.lo + lo.hi, A negated through the
-//      instruction descriptor) — fp32 accumulation in place in TMEM.
-// Back substitution L^T x = z runs block-wise from the bottom: the owners of the
-// already-final x multiply their rows of block column j, a shuffle reduce-scatter
-// sums the 16 lanes, warp j finishes with the transposed triangular solve.
+//   3. one elected lane per warp issues, for "its" system, D[:, 16(j+1):] -= X X^T as
+//      hi.hi + hi.lo + lo.hi — six tcgen05.mma.kind::tf32 (K = 8 each, A negated
+//      through the instruction descriptor), fp32 accumulation in place in TMEM;
+//      only the warp that factors the next diagonal block polls their mbarrier.
+// Back substitution L^T x = z runs block-wise from the bottom: warp j takes the
+// contributions of the finished blocks off its right-hand side, solves its
+// transposed 16x16 block (every lane redundantly, from broadcast reads of L_jj),
+// multiplies its rows of block column j-1 by x_j and sums them over the 16 lanes
+// (shuffle reduce-scatter) before the barrier — the one contribution warp j-1 is
+// still missing — and the older block columns after it.
+// GJ = true (solve4's template flag) is the block Gauss-Jordan variant described there.
 #pragma once
 
 #include "tc_common.cuh"
