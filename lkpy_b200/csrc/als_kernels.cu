@@ -425,13 +425,26 @@ __global__ void __launch_bounds__(256) otor_partial_kernel(const float *__restri
 __global__ void otor_reduce_kernel(const float *__restrict__ partial, int nblocks, int KP, int k,
                                    float reg, float *__restrict__ out)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= k * k) return;
-    const int i = e / k, j = e % k;
+    // a block of 8 warps owns 32 consecutive output elements: warp g sums the partials g, g+8, ...
+    // (coalesced 128-byte reads), warp 0 adds the eight sums in fixed order — deterministic, and
+    // an eighth of the dependent loads per thread of the one-thread-per-element version
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
+    const bool live = e < k * k;
+    const int i = live ? e / k : 0, j = live ? e % k : 0;
     float s = 0.0f;
-    for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * KP * KP + i * KP + j];
-    if (i == j) s += reg;
-    out[e] = s;
+    if (live)
+        for (int b = g; b < nblocks; b += 8) s += partial[(size_t)b * KP * KP + i * KP + j];
+    part[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && live) {
+        float t = part[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; w++) t += part[w][lane];
+        if (i == j) t += reg;
+        out[e] = t;
+    }
 }
 
 int launch_als_tc(const lk_als_args &a, cudaStream_t st);   // als_tc.cu  (tensor-core Gram, shared-memory solve)
@@ -608,7 +621,7 @@ int lk_als_otor(const float *d_other, int64_t n_other, int32_t k, float reg, flo
         default: otor_partial_kernel<128><<<grid, 256, 0, st>>>(d_other, n_other, k, d_scratch, obf); break;
     }
     LK_CUDA_TRY(cudaGetLastError());
-    otor_reduce_kernel<<<(k * k + 255) / 256, 256, 0, st>>>(d_scratch, grid, kp, k, reg, d_otor);
+    otor_reduce_kernel<<<(k * k + 31) / 32, 256, 0, st>>>(d_scratch, grid, kp, k, reg, d_otor);
     LK_CUDA_TRY(cudaGetLastError());
     return LK_OK;
 }
