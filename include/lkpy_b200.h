@@ -222,6 +222,13 @@ typedef struct lk_knn_score_args {
     int32_t *d_counts;           /* [n_targets] -1 = null */
     int32_t *d_work_counter;     /* [1] zeroed by the call */
     int32_t *d_status;           /* [1] 0 ok; 2 NaN similarity */
+    /* Per-warp heap states for the targets that receive more than max_nbrs contributions
+     * (accum.rs:100-117): [slotmap_warps * heap_floats_per_warp] 32-bit words, 8-byte aligned;
+     * one target takes 2 + 2*(max_nbrs+1) words.  Optional (NULL / 0): targets that do not fit are
+     * replayed one at a time from the query's history instead (same result, much slower for long
+     * histories). */
+    float *d_heap_scratch;
+    int64_t heap_floats_per_warp;
 } lk_knn_score_args;
 
 /* number of warps the scoring grid runs (one slotmap row each) */

@@ -125,6 +125,8 @@ class LkKnnScoreArgs(C.Structure):
         ("d_counts", vp),
         ("d_work_counter", vp),
         ("d_status", vp),
+        ("d_heap_scratch", vp),
+        ("heap_floats_per_warp", C.c_int64),
     ]
 
 

@@ -73,13 +73,45 @@ __device__ void heap_pop(AccEnt *d, int &len)
 
 constexpr int SCORE_MAX_NBRS = 128;  // heap re-scoring keeps max_nbrs+1 entries in local memory
 
-// exact ScoreAccumulator replay for one (query, target) pair
+// One contribution into a ScoreAccumulator (accum.rs:86-117): vector until `limit` entries,
+// then the Partial -> Full switch (pop from the back, push: accum.rs:73-82 — done in place by
+// reversing the array and sifting the elements up one after the other, the same sequence of
+// pushes), then Rust's BinaryHeap push / pop on the weight-reversed order.
+__device__ void acc_push(AccEnt *d, int &len, int &is_heap, const AccEnt e, const int limit)
+{
+    if (!is_heap && len < limit) {
+        d[len++] = e;
+        return;
+    }
+    if (!is_heap) {
+        const int n = len;
+        for (int i = 0; i < n / 2; i++) {
+            const AccEnt t = d[i];
+            d[i] = d[n - 1 - i];
+            d[n - 1 - i] = t;
+        }
+        for (int m = 1; m < n; m++) heap_sift_up(d, 0, m);
+        is_heap = 1;
+    }
+    if (e.w > d[0].w) {  // accum.rs:107
+        d[len++] = e;
+        heap_sift_up(d, 0, len - 1);
+        while (len > limit) heap_pop(d, len);
+    }
+}
+
+// per-target heap state kept in the per-warp scratch of lk_knn_score_args::d_heap_scratch:
+// [len, is_heap, (w, v) x (limit + 1)] as 32-bit words
+__device__ __forceinline__ int heap_state_words(int limit) { return 2 + 2 * (limit + 1); }
+
+// exact ScoreAccumulator replay for one (query, target) pair (fallback when the per-warp heap
+// scratch is absent or full)
 __device__ void rescore_exact(const lk_knn_score_args &a, int64_t r0, int64_t r1, int t, float *out_ws,
                               float *out_tw, int *out_len)
 {
     AccEnt d[SCORE_MAX_NBRS + 1];
     int len = 0;
-    bool is_heap = false;
+    int is_heap = 0;
     const int limit = a.max_nbrs;
     for (int64_t p = r0; p < r1; p++) {
         const int r = a.d_ref_items[p];
@@ -94,26 +126,7 @@ __device__ void rescore_exact(const lk_knn_score_args &a, int64_t r0, int64_t r1
         AccEnt e;
         e.w = a.d_sim_vals[lo];
         e.v = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
-        if (!is_heap && len < limit) {
-            d[len++] = e;
-        } else {
-            if (!is_heap) {  // Partial -> Full: pop from the back, push (accum.rs:73-82)
-                AccEnt tmp[SCORE_MAX_NBRS + 1];
-                const int n = len;
-                for (int i = 0; i < n; i++) tmp[i] = d[i];
-                len = 0;
-                for (int i = n - 1; i >= 0; i--) {
-                    d[len++] = tmp[i];
-                    heap_sift_up(d, 0, len - 1);
-                }
-                is_heap = true;
-            }
-            if (e.w > d[0].w) {  // accum.rs:107
-                d[len++] = e;
-                heap_sift_up(d, 0, len - 1);
-                while (len > limit) heap_pop(d, len);
-            }
-        }
+        acc_push(d, len, is_heap, e, limit);
     }
     float tw = 0.0f, ws = 0.0f;
     for (int i = 0; i < len; i++) tw = __fadd_rn(tw, d[i].w);
@@ -130,6 +143,11 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
     int32_t *slotmap = a.d_slotmap + (size_t)gwarp * a.n_items;
     const bool explicit_fb = a.d_ref_vals != nullptr;
     const float qnan = __int_as_float(0x7fc00000);
+    const int hwords = heap_state_words(a.max_nbrs);
+    uint32_t *heap_base = a.d_heap_scratch != nullptr
+                              ? reinterpret_cast<uint32_t *>(a.d_heap_scratch) + (size_t)gwarp * a.heap_floats_per_warp
+                              : nullptr;
+    const int heap_cap = a.d_heap_scratch != nullptr ? (int)(a.heap_floats_per_warp / hwords) : 0;
 
     for (;;) {
         int q = 0;
@@ -173,6 +191,51 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
             __syncwarp();
         }
 
+        // 2b. targets that received more than max_nbrs contributions have left the vector state:
+        //     give each a heap in this warp's scratch (marker -(index+2) in its count) and run the
+        //     history once more, every lane pushing its entry into its target's heap — the same
+        //     element movement as the reference's accumulator, in the same order.  Targets that do
+        //     not fit the scratch keep their count and are replayed one by one in step 3.
+        if (heap_base != nullptr) {
+            int n_tracked = 0;  // warp-uniform running count
+            for (int64_t x0 = t0; x0 < t1; x0 += 32) {
+                const int64_t x = x0 + lane;
+                const bool over = x < t1 && a.d_acc_cnt[x] > a.max_nbrs;
+                const unsigned m = __ballot_sync(FULL, over);
+                if (m == 0u) continue;
+                const int idx = n_tracked + __popc(m & ((1u << lane) - 1u));
+                if (over && idx < heap_cap) {
+                    a.d_acc_cnt[x] = -(idx + 2);
+                    uint32_t *hs = heap_base + (size_t)idx * hwords;
+                    hs[0] = 0u, hs[1] = 0u;
+                }
+                n_tracked += __popc(m);
+            }
+            __syncwarp();
+            if (n_tracked > 0) {
+                for (int64_t p = r0; p < r1; p++) {
+                    const int r = a.d_ref_items[p];
+                    if (r < 0 || r >= a.n_items) continue;
+                    const float rv = explicit_fb ? a.d_ref_vals[p] : 0.0f;
+                    const int64_t s0 = a.d_sim_indptr[r], s1 = a.d_sim_indptr[r + 1];
+                    for (int64_t e = s0 + lane; e < s1; e += 32) {
+                        const int32_t slot = slotmap[a.d_sim_cols[e]];
+                        if (slot < 0) continue;
+                        const int mk = a.d_acc_cnt[t0 + slot];
+                        if (mk > -2) continue;
+                        uint32_t *hs = heap_base + (size_t)(-mk - 2) * hwords;
+                        int len = (int)hs[0], is_heap = (int)hs[1];
+                        AccEnt ent;
+                        ent.w = a.d_sim_vals[e];
+                        ent.v = rv;
+                        acc_push(reinterpret_cast<AccEnt *>(hs + 2), len, is_heap, ent, a.max_nbrs);
+                        hs[0] = (uint32_t)len, hs[1] = (uint32_t)is_heap;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+
         // 3. finalise every target position (duplicate targets read the registered slot)
         for (int64_t x = t0 + lane; x < t1; x += 32) {
             const int t = a.d_tgt_items[x];
@@ -182,7 +245,16 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
                 const int64_t xs = t0 + slotmap[t];
                 int c = a.d_acc_cnt[xs];
                 float ws = a.d_acc_ws[xs], tw = a.d_acc_tw[xs];
-                if (c > a.max_nbrs) rescore_exact(a, r0, r1, t, &ws, &tw, &c);  // heap state
+                if (c <= -2) {  // heap state built in step 2b: sums in heap-array order
+                    const uint32_t *hs = heap_base + (size_t)(-c - 2) * hwords;
+                    const AccEnt *d = reinterpret_cast<const AccEnt *>(hs + 2);
+                    c = (int)hs[0];
+                    tw = 0.0f, ws = 0.0f;
+                    for (int i = 0; i < c; i++) tw = __fadd_rn(tw, d[i].w);
+                    for (int i = 0; i < c; i++) ws = __fadd_rn(ws, __fmul_rn(d[i].w, d[i].v));
+                } else if (c > a.max_nbrs) {
+                    rescore_exact(a, r0, r1, t, &ws, &tw, &c);  // heap state, replayed from scratch
+                }
                 count = c;
                 if (c >= a.min_nbrs) score = explicit_fb ? ws / tw : tw;
             }

@@ -377,6 +377,16 @@ class KnnScorerState:
     slotmap_warps: int
     work_counter: torch.Tensor
     status: torch.Tensor
+    heap_scratch: dict = field(default_factory=dict)  # max_nbrs -> per-warp heap states (allocated on first use)
+    HEAP_TARGETS_PER_WARP = 2048
+
+    def _heap(self, max_nbrs: int) -> tuple[torch.Tensor, int]:
+        per_warp = self.HEAP_TARGETS_PER_WARP * (2 + 2 * (int(max_nbrs) + 1))
+        t = self.heap_scratch.get(int(max_nbrs))
+        if t is None:
+            t = torch.empty(self.slotmap_warps * per_warp, dtype=torch.float32, device=self.sim_cols.device)
+            self.heap_scratch[int(max_nbrs)] = t
+        return t, per_warp
 
     @classmethod
     def create(cls, n_items: int, indptr, cols, vals, device=None) -> "KnnScorerState":
@@ -429,6 +439,8 @@ class KnnScorerState:
         a.d_acc_ws, a.d_acc_tw, a.d_acc_cnt = ptr(acc_ws), ptr(acc_tw), ptr(acc_cnt)
         a.d_scores, a.d_counts = ptr(scores), ptr(counts)
         a.d_work_counter, a.d_status = ptr(self.work_counter), ptr(self.status)
+        heap, per_warp = self._heap(max_nbrs)
+        a.d_heap_scratch, a.heap_floats_per_warp = ptr(heap), per_warp
         check(lib().lk_knn_score_batch(C.byref(a), stream_ptr()), "lk_knn_score_batch")
         # keep scratch alive until the stream has consumed it
         torch.cuda.current_stream().synchronize()

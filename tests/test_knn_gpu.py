@@ -118,6 +118,15 @@ def _score_gpu(S, queries, max_nbrs, min_nbrs, explicit=True):
     return sc.cpu().numpy(), ct.cpu().numpy(), tgt_ptr
 
 
+@pytest.mark.parametrize("heap_cap", [2048, 2, 0])
+def test_score_heap_scratch_sizes(cuda_lib, ml_small, monkeypatch, heap_cap):
+    """Targets beyond max_nbrs keep their heap in the per-warp scratch (step 2b of the kernel); when
+    it is too small (2 targets) or absent (0) the rest is replayed one by one — same bits either way."""
+    monkeypatch.setattr(engine.KnnScorerState, "HEAP_TARGETS_PER_WARP", heap_cap)
+    test_score_matches_oracle_exactly(cuda_lib, ml_small, True, 5, None)
+    test_score_matches_oracle_exactly(cuda_lib, ml_small, False, 3, None)
+
+
 @pytest.mark.parametrize("explicit", [True, False])
 @pytest.mark.parametrize("max_nbrs,save_nbrs", [(20, None), (5, None), (20, 20), (3, 50)])
 def test_score_matches_oracle_exactly(cuda_lib, ml_small, explicit, max_nbrs, save_nbrs):
