@@ -163,6 +163,18 @@ def ncu_traffic(key: str, world: int) -> float | None:
 # ---------------------------------------------------------------------------
 
 
+def host_threads() -> int:
+    """
+    Host threads the CPU arm may use: the cores this process may run on.  (Not OMP_NUM_THREADS:
+    torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently turn the multi-threaded
+    CPU baseline into a single-threaded one whenever the bench is launched under it.)
+    """
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 def _slice_rows(csr, lo: int, hi: int):
     from lkpy_b200.data import InteractionCSR
 
@@ -273,7 +285,7 @@ def run_reference(args, rank: int) -> None:
     rng = np.random.default_rng(0)
     p = (rng.standard_normal((inter.n_users, K)) * 0.1).astype(np.float32)
     q = (rng.standard_normal((inter.n_items, K)) * 0.1).astype(np.float32)
-    threads = oracle.max_threads()
+    threads = host_threads()
     per_step = max(4.0, 120.0 / max(args.steps + args.warmup, 1))
     vals = []
     sample = ""
@@ -481,7 +493,7 @@ def main() -> None:
     if not args.no_cpu and rank == 0 and world == 1:
         import oracle
 
-        threads = oracle.max_threads()
+        threads = host_threads()
         ui, iu = data.als_implicit_matrices(inter, WEIGHT)
         rng = np.random.default_rng(0)
         p = (rng.standard_normal((inter.n_users, K)) * 0.1).astype(np.float32)
