@@ -229,6 +229,15 @@ typedef struct lk_knn_score_args {
      * histories). */
     float *d_heap_scratch;
     int64_t heap_floats_per_warp;
+    /* Contribution pool (optional; with it the list-based kernel runs: per-target contribution
+     * lists built in parallel, sorted by history position, replayed — same bits, no sequential
+     * walk over the history).  pool_entries 16-byte entries, at least the number of
+     * (reference item, similarity-row entry) pairs of the whole batch:
+     * sum over valid d_ref_items r of (d_sim_indptr[r+1] - d_sim_indptr[r]); d_pool_cursor [1]
+     * is zeroed by the call.  Status 3 = pool too small. */
+    void *d_pool;
+    int64_t pool_entries;
+    unsigned long long *d_pool_cursor;
 } lk_knn_score_args;
 
 /* number of warps the scoring grid runs (one slotmap row each) */

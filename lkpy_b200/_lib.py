@@ -127,6 +127,9 @@ class LkKnnScoreArgs(C.Structure):
         ("d_status", vp),
         ("d_heap_scratch", vp),
         ("heap_floats_per_warp", C.c_int64),
+        ("d_pool", vp),
+        ("pool_entries", C.c_int64),
+        ("d_pool_cursor", vp),
     ]
 
 

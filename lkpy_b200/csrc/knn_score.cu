@@ -270,6 +270,252 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// List-based variant (used when lk_knn_score_args::d_pool is given): no sequential walk over the
+// history.  Contributions are counted per target with the 32 lanes working on 32 history entries at
+// once, a prefix sum lays the targets' lists out in a pool, a second parallel pass fills the lists
+// (chunks of 32 history entries are committed in order, so a list is sorted up to displacements
+// inside one chunk), and every target then sorts its list by history position and replays it
+// through the accumulator — vector sums in push order, BinaryHeap movement past max_nbrs — exactly
+// as the sequential kernel does.  A query's cost no longer grows with the length of its history
+// times a global-memory round trip.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) PoolEnt {
+    int32_t pos;  // index of the reference item in the query's history
+    float sim, rv;
+    int32_t pad;
+};
+
+__global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int32_t *slotmap = a.d_slotmap + (size_t)gwarp * a.n_items;
+    const bool explicit_fb = a.d_ref_vals != nullptr;
+    const float qnan = __int_as_float(0x7fc00000);
+    int32_t *acc_cnt = a.d_acc_cnt;
+    int32_t *acc_off = reinterpret_cast<int32_t *>(a.d_acc_ws);  // list offset of a target (scratch reuse)
+    int32_t *acc_cur = reinterpret_cast<int32_t *>(a.d_acc_tw);  // fill cursor of a target
+    PoolEnt *pool = reinterpret_cast<PoolEnt *>(a.d_pool);
+    const int limit = a.max_nbrs;
+
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(a.d_work_counter, 1);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= a.n_queries) break;
+        const int64_t t0 = a.d_tgt_indptr[q], t1 = a.d_tgt_indptr[q + 1];
+        const int64_t r0 = a.d_ref_indptr[q], r1 = a.d_ref_indptr[q + 1];
+
+        // The passes over the target list (steps 1, 3, 5, 6) are latency-bound streams over per-query
+        // arrays that live in DRAM: UB independent loads per lane are kept in flight.
+        constexpr int UB = 8;
+
+        // 1. register the targets
+        for (int64_t xb = t0 + lane; xb < t1; xb += 32 * UB) {
+            int tt[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) tt[u] = xb + 32 * u < t1 ? __ldg(a.d_tgt_items + xb + 32 * u) : -1;
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int64_t x = xb + 32 * u;
+                if (x < t1) {
+                    acc_cnt[x] = 0;
+                    if (tt[u] >= 0 && tt[u] < a.n_items) slotmap[tt[u]] = (int32_t)(x - t0);
+                }
+            }
+        }
+        __syncwarp();
+
+        // 2. count the contributions per target: one history entry per lane
+        for (int64_t p0 = r0; p0 < r1; p0 += 32) {
+            const int64_t p = p0 + lane;
+            if (p < r1) {
+                const int r = a.d_ref_items[p];
+                if (r >= 0 && r < a.n_items) {
+                    const int64_t s1 = a.d_sim_indptr[r + 1];
+                    for (int64_t e = a.d_sim_indptr[r]; e < s1; e += UB) {  // UB entries of the row in flight
+                        int cc[UB], sl[UB];
+                        float sv[UB];
+#pragma unroll
+                        for (int u = 0; u < UB; u++) {
+                            cc[u] = e + u < s1 ? __ldg(a.d_sim_cols + e + u) : -1;
+                            sv[u] = e + u < s1 ? __ldg(a.d_sim_vals + e + u) : 0.0f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB; u++) sl[u] = cc[u] >= 0 ? slotmap[cc[u]] : -1;
+#pragma unroll
+                        for (int u = 0; u < UB; u++) {
+                            if (sl[u] >= 0) {
+                                if (sv[u] != sv[u]) atomicCAS(a.d_status, 0, 2);  // "similarity is null"
+                                atomicAdd(&acc_cnt[t0 + sl[u]], 1);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // 3. lay the lists out: exclusive prefix sum of the counts, one pool segment per query
+        int running = 0;
+        for (int64_t x0 = t0; x0 < t1; x0 += 32 * UB) {
+            int cc[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int64_t x = x0 + 32 * u + lane;
+                cc[u] = x < t1 ? __ldcg(&acc_cnt[x]) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int64_t x = x0 + 32 * u + lane;
+                const int incl = warp_incl_scan(cc[u], lane);
+                if (x < t1) {
+                    acc_off[x] = running + incl - cc[u];
+                    acc_cur[x] = 0;
+                }
+                running += __shfl_sync(FULL, incl, 31);
+            }
+        }
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.d_pool_cursor, (unsigned long long)running);
+        base = __shfl_sync(FULL, base, 0);
+        const bool fits = base + (unsigned long long)running <= (unsigned long long)a.pool_entries;
+        if (!fits && lane == 0) atomicCAS(a.d_status, 0, 3);  // pool too small (caller sizing error)
+        __syncwarp();
+
+        // 4. fill the lists; chunks of 32 history entries are committed in order
+        if (fits) {
+            for (int64_t p0 = r0; p0 < r1; p0 += 32) {
+                const int64_t p = p0 + lane;
+                if (p < r1) {
+                    const int r = a.d_ref_items[p];
+                    if (r >= 0 && r < a.n_items) {
+                        const float rv = explicit_fb ? a.d_ref_vals[p] : 0.0f;
+                        const int64_t s1 = a.d_sim_indptr[r + 1];
+                        for (int64_t e = a.d_sim_indptr[r]; e < s1; e += UB) {
+                            int cc[UB], sl[UB], of[UB], kp[UB];
+                            float sv[UB];
+#pragma unroll
+                            for (int u = 0; u < UB; u++) {
+                                cc[u] = e + u < s1 ? __ldg(a.d_sim_cols + e + u) : -1;
+                                sv[u] = e + u < s1 ? __ldg(a.d_sim_vals + e + u) : 0.0f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < UB; u++) sl[u] = cc[u] >= 0 ? slotmap[cc[u]] : -1;
+#pragma unroll
+                            for (int u = 0; u < UB; u++) {
+                                of[u] = sl[u] >= 0 ? acc_off[t0 + sl[u]] : 0;
+                                kp[u] = sl[u] >= 0 ? atomicAdd(&acc_cur[t0 + sl[u]], 1) : 0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < UB; u++) {
+                                if (sl[u] >= 0) {
+                                    PoolEnt ent;
+                                    ent.pos = (int32_t)(p - r0);
+                                    ent.sim = sv[u];
+                                    ent.rv = rv;
+                                    ent.pad = 0;
+                                    pool[base + (unsigned long long)(of[u] + kp[u])] = ent;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+
+        // 5. every registered target sorts its list by history position and replays it; null targets
+        //    are answered on the way, duplicates of a target are left for step 5b
+        bool any_dup = false;
+        for (int64_t xb = t0 + lane; xb < t1; xb += 32 * UB) {
+            int tt[UB], sm[UB], nn[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) tt[u] = xb + 32 * u < t1 ? __ldg(a.d_tgt_items + xb + 32 * u) : -1;
+#pragma unroll
+            for (int u = 0; u < UB; u++) sm[u] = (tt[u] >= 0 && tt[u] < a.n_items) ? slotmap[tt[u]] : -1;
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int64_t x = xb + 32 * u;
+                nn[u] = (fits && sm[u] >= 0 && t0 + sm[u] == x) ? __ldcg(&acc_cnt[x]) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int64_t x = xb + 32 * u;
+                if (x >= t1) continue;
+                if (sm[u] < 0) {  // null (or out-of-range) target
+                    a.d_scores[x] = qnan;
+                    a.d_counts[x] = -1;
+                    continue;
+                }
+                if (t0 + sm[u] != x) {
+                    any_dup = true;
+                    continue;
+                }
+                const int n = nn[u];
+                float ws = 0.0f, tw = 0.0f;
+                int c = n;
+                if (n > 0) {
+                    PoolEnt *L = pool + base + (unsigned long long)acc_off[x];
+                    for (int i = 1; i < n; i++) {  // insertion sort: displacements stay inside a 32-entry chunk
+                        const PoolEnt key = L[i];
+                        int j = i - 1;
+                        while (j >= 0 && L[j].pos > key.pos) {
+                            L[j + 1] = L[j];
+                            j--;
+                        }
+                        L[j + 1] = key;
+                    }
+                    if (n <= limit) {  // vector state: sums in push order (accum.rs:86-98, 196-231)
+                        for (int i = 0; i < n; i++) tw = __fadd_rn(tw, L[i].sim);
+                        if (explicit_fb)
+                            for (int i = 0; i < n; i++) ws = __fadd_rn(ws, __fmul_rn(L[i].sim, L[i].rv));
+                    } else {
+                        AccEnt d[SCORE_MAX_NBRS + 1];
+                        int len = 0, is_heap = 0;
+                        for (int i = 0; i < n; i++) {
+                            AccEnt ent;
+                            ent.w = L[i].sim;
+                            ent.v = L[i].rv;
+                            acc_push(d, len, is_heap, ent, limit);
+                        }
+                        for (int i = 0; i < len; i++) tw = __fadd_rn(tw, d[i].w);
+                        for (int i = 0; i < len; i++) ws = __fadd_rn(ws, __fmul_rn(d[i].w, d[i].v));
+                        c = len;
+                    }
+                }
+                a.d_counts[x] = c;
+                a.d_scores[x] = (c >= a.min_nbrs) ? (explicit_fb ? ws / tw : tw) : qnan;
+            }
+        }
+        __syncwarp();
+        // 5b. duplicate targets copy the registered position's result (rare: skipped when there are none)
+        if (__any_sync(FULL, any_dup)) {
+            for (int64_t x = t0 + lane; x < t1; x += 32) {
+                const int t = a.d_tgt_items[x];
+                if (t >= 0 && t < a.n_items && t0 + slotmap[t] != x) {
+                    a.d_scores[x] = a.d_scores[t0 + slotmap[t]];
+                    a.d_counts[x] = a.d_counts[t0 + slotmap[t]];
+                }
+            }
+            __syncwarp();
+        }
+        // 6. leave the slot map at -1
+        for (int64_t xb = t0 + lane; xb < t1; xb += 32 * UB) {
+            int tt[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) tt[u] = xb + 32 * u < t1 ? __ldg(a.d_tgt_items + xb + 32 * u) : -1;
+#pragma unroll
+            for (int u = 0; u < UB; u++)
+                if (tt[u] >= 0 && tt[u] < a.n_items) slotmap[tt[u]] = -1;
+        }
+        __syncwarp();
+    }
+}
+
 constexpr int SCORE_WARPS_PER_SM = 16;
 
 }  // namespace lk
@@ -296,7 +542,16 @@ int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LK_CUDA_TRY(cudaMemsetAsync(a.d_work_counter, 0, sizeof(int32_t), st));
     const int blocks = sm_count() * SCORE_WARPS_PER_SM / 8;
-    knn_score_kernel<<<blocks, 256, 0, st>>>(a);
+    // with a contribution pool the list-based kernel runs (LK_KNN_SCORE_SEQ=1 forces the sequential one)
+    const char *seq = getenv("LK_KNN_SCORE_SEQ");
+    if (a.d_pool != nullptr && a.d_pool_cursor != nullptr && !(seq && seq[0] == '1')) {
+        LK_REQUIRE(reinterpret_cast<uintptr_t>(a.d_pool) % 16 == 0 && a.pool_entries >= 0, LK_ERR_INVALID,
+                   "lk_knn_score_batch: bad contribution pool");
+        LK_CUDA_TRY(cudaMemsetAsync(a.d_pool_cursor, 0, sizeof(unsigned long long), st));
+        knn_score_lists_kernel<<<blocks, 256, 0, st>>>(a);
+    } else {
+        knn_score_kernel<<<blocks, 256, 0, st>>>(a);
+    }
     LK_CUDA_TRY(cudaGetLastError());
     return LK_OK;
 }

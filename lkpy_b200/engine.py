@@ -379,6 +379,7 @@ class KnnScorerState:
     status: torch.Tensor
     heap_scratch: dict = field(default_factory=dict)  # max_nbrs -> per-warp heap states (allocated on first use)
     HEAP_TARGETS_PER_WARP = 2048
+    USE_LISTS = True  # list-based kernel (parallel over the history); False: the sequential kernel
 
     def _heap(self, max_nbrs: int) -> tuple[torch.Tensor, int]:
         per_warp = self.HEAP_TARGETS_PER_WARP * (2 + 2 * (int(max_nbrs) + 1))
@@ -441,11 +442,28 @@ class KnnScorerState:
         a.d_work_counter, a.d_status = ptr(self.work_counter), ptr(self.status)
         heap, per_warp = self._heap(max_nbrs)
         a.d_heap_scratch, a.heap_floats_per_warp = ptr(heap), per_warp
+        if self.USE_LISTS and ref_items.numel() > 0:
+            # contribution pool for the list-based kernel: one 16-byte entry per (reference item,
+            # similarity-row entry) pair of the batch
+            r = ref_items.long()
+            ok = (r >= 0) & (r < self.n_items)
+            rr = r.clamp(0, self.n_items - 1)
+            total = int(((self.sim_indptr[rr + 1] - self.sim_indptr[rr]) * ok).sum().item())
+            pool = self.heap_scratch.get("pool")
+            if pool is None or pool.numel() < 4 * max(total, 1):
+                pool = torch.empty(4 * max(total, 1), dtype=torch.int32, device=dev)
+                self.heap_scratch["pool"] = pool
+                self.heap_scratch["pool_cursor"] = torch.zeros(1, dtype=torch.int64, device=dev)
+            a.d_pool, a.pool_entries = ptr(pool), pool.numel() // 4
+            a.d_pool_cursor = ptr(self.heap_scratch["pool_cursor"])
         check(lib().lk_knn_score_batch(C.byref(a), stream_ptr()), "lk_knn_score_batch")
         # keep scratch alive until the stream has consumed it
         torch.cuda.current_stream().synchronize()
-        if int(self.status.item()) == 2:
+        st = int(self.status.item())
+        if st == 2:
             raise ValueError("similarity is null")
+        if st == 3:
+            raise _lib.EngineError("lk_knn_score_batch: contribution pool too small")
         return scores[:nt], counts[:nt]
 
 

@@ -123,8 +123,10 @@ def test_score_heap_scratch_sizes(cuda_lib, ml_small, monkeypatch, heap_cap):
     """Targets beyond max_nbrs keep their heap in the per-warp scratch (step 2b of the kernel); when
     it is too small (2 targets) or absent (0) the rest is replayed one by one — same bits either way."""
     monkeypatch.setattr(engine.KnnScorerState, "HEAP_TARGETS_PER_WARP", heap_cap)
+    monkeypatch.setattr(engine.KnnScorerState, "USE_LISTS", False)  # the sequential kernel
     test_score_matches_oracle_exactly(cuda_lib, ml_small, True, 5, None)
     test_score_matches_oracle_exactly(cuda_lib, ml_small, False, 3, None)
+    test_score_matches_oracle_exactly(cuda_lib, ml_small, True, 20, 20)
 
 
 @pytest.mark.parametrize("explicit", [True, False])
