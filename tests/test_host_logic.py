@@ -63,3 +63,25 @@ def test_committed_bench_lines_have_the_contract_keys():
     ref = json.loads((ROOT / "profiles" / "r01_final_bench_reference_arm.json").read_text().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0
     assert {"kind", "cores", "sample", "value"} <= set(ref["cpu_baseline"])
+
+
+def test_solve_cholesky_property():
+    """The reference's property test of `solve_cholesky` (tests/utils/test_math_solve.py:21-50) against the
+    host fold-in solver that mirrors it (`lkpy_b200.als._solve_cholesky`)."""
+    import numpy as np
+    from pytest import approx
+
+    from lkpy_b200.als import _solve_cholesky
+
+    for seed in range(40):
+        rng = np.random.RandomState(seed)
+        size = int(rng.randint(2, 101))
+        A = rng.randn(size, size) * 10
+        b = rng.randn(size) * 10
+        A = A * A
+        xexp = np.linalg.lstsq(A, b, rcond=None)[0]
+        F, y = A.T @ A, A.T @ b
+        x = _solve_cholesky(F, y)
+        assert x.shape == y.shape
+        assert x == approx(xexp, rel=1.0e-3)
+        assert F @ x == approx(y, rel=2.0e-6, abs=5.0e-9)
