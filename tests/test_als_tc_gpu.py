@@ -154,3 +154,25 @@ def test_tc_non_uniform_weights_fall_back(cuda_lib, monkeypatch):
     assert not plan.vals_uniform
     ref, _ = _oracle("implicit", ui, p, q, 0.1)
     assert rel_fro(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("variant", ["tc-cholesky", "tc-gauss-jordan", "smem-solve"])
+def test_tc_not_positive_definite_is_reported(cuda_lib, monkeypatch, variant):
+    """A system that is not positive definite (the reference's `ALS solve error`, implicit.rs:79) sets the
+    status word and leaves the row untouched — also on the tensor-core path."""
+    _set(monkeypatch, variant)
+    inter = small_synth(60, 40, 600, seed=2)
+    ui, _ = data.als_implicit_matrices(inter, 40.0)
+    dev = _lib.require_device()
+    k = 64
+    dm = engine.DeviceCSR.from_host(ui, dev)
+    plan = engine.ALSHalfPlan.create(dm, k)
+    assert plan.vals_uniform
+    this = torch.full((60, k), 0.5, device=dev)
+    other = torch.zeros((40, k), device=dev, dtype=torch.bfloat16)
+    otor = -torch.eye(k, device=dev)
+    engine.als_half_epoch(plan, _lib.LK_ALS_IMPLICIT, this, other, otor=otor)
+    torch.cuda.synchronize()
+    assert int(plan.status.item()) > 0
+    nonempty = torch.from_numpy(np.diff(ui.indptr) > 0).to(dev)
+    assert torch.all(this[nonempty] == 0.5)  # failed solves do not write
