@@ -12,7 +12,12 @@ item half-epoch, each = OtOr kernel + row-solve kernel, + the factor all-gather
 when N > 1) over the resident CSR matrices.  `value` is the epoch time with
 everything resident in HBM; `e2e` is the same epoch through the public trainer
 API with the factor tables coming from / going back to pinned host memory inside
-the timed region.  The item-kNN numbers ride along under "knn".
+the timed region.  Riding along: "als_fp32" (the same epoch with fp32 gathered rows),
+"knn" (item-kNN build items/s with its kernel roofline and CPU figure, batched
+scoring users/s) and, at N=1, "recommend" (batched scoring + top-100 users/s with
+the selection kernel's roofline and the per-query CPU figure).  "cpu_baseline" and
+`--impl reference` time the CPU restatement of the reference path (oracle/) on a
+bounded sample at its best thread count.  Only the JSON line goes to stdout.
 """
 
 from __future__ import annotations
