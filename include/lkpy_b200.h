@@ -65,6 +65,13 @@ LK_API int lk_version(void);
 LK_API const char *lk_last_error(void);
 /* Number of SMs and compute capability (major*10+minor) of the current device. */
 LK_API int lk_device_info(int *sm_count, int *cc);
+/* Diagnostic switches (kernel variants kept for comparison; none changes results beyond rounding).
+ * Each is also an environment variable of the same name, read once when the library first needs
+ * it — never per launch; after that only lk_set_option changes it.  Names: LK_ALS_TC,
+ * LK_ALS_TC_INTERLEAVE, LK_ALS_TC_OCC, LK_ALS_TCS, LK_ALS_GJ, LK_ALS_TF32, LK_KNN_WARPS,
+ * LK_KNN_CTAS, LK_KNN_SCORE_SEQ (meaning: lkpy_b200/csrc/common.cuh, struct Options). */
+LK_API int lk_set_option(const char *name, int value);
+LK_API int lk_get_option(const char *name, int *value);
 
 /* ------------------------------------------------------------------------- */
 /* ALS                                                                        */
@@ -215,7 +222,8 @@ typedef struct lk_knn_score_args {
     const int32_t *d_tgt_items;  /* negative = null -> score NaN, count -1 */
     int32_t max_nbrs, min_nbrs;
     int32_t *d_slotmap;          /* [slotmap_warps * n_items], all -1 on entry and on exit */
-    int64_t slotmap_warps;       /* >= lk_knn_score_warps() */
+    int64_t slotmap_warps;       /* warps that work on the batch, one slot-map row each: 1..lk_knn_score_warps()
+                                    (more is not used); min(n_queries, lk_knn_score_warps()) is enough */
     float *d_acc_ws, *d_acc_tw;  /* [n_targets] accumulator scratch */
     int32_t *d_acc_cnt;          /* [n_targets] */
     float *d_scores;             /* [n_targets] NaN = null (Arrow null in the reference) */
@@ -240,7 +248,7 @@ typedef struct lk_knn_score_args {
     unsigned long long *d_pool_cursor;
 } lk_knn_score_args;
 
-/* number of warps the scoring grid runs (one slotmap row each) */
+/* largest number of warps the scoring grid runs (one slotmap row each) */
 LK_API int64_t lk_knn_score_warps(void);
 LK_API int lk_knn_score_batch(const lk_knn_score_args *args, void *stream);
 

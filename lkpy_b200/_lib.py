@@ -138,6 +138,8 @@ SYMBOLS: dict[str, tuple] = {
     "lk_version": (C.c_int, []),
     "lk_last_error": (C.c_char_p, []),
     "lk_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "lk_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "lk_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "lk_als_max_features": (C.c_int, []),
     "lk_als_plan_size": (C.c_int, [vp, C.c_int64, C.c_int32, i64p, i64p, i64p]),
     "lk_als_plan_fill": (C.c_int, [vp, C.c_int64, C.c_int32, vp]),
@@ -177,6 +179,17 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def set_option(name: str, value: int) -> None:
+    """Switch a diagnostic kernel variant (``lk_set_option``; the LK_* environment is read once at load)."""
+    check(lib().lk_set_option(name.encode(), int(value)), "lk_set_option")
+
+
+def get_option(name: str) -> int:
+    v = C.c_int()
+    check(lib().lk_get_option(name.encode(), C.byref(v)), "lk_get_option")
+    return int(v.value)
 
 
 def check(rc: int, what: str = "") -> None:

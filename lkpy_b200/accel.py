@@ -117,18 +117,23 @@ def as_host_csr(m: Any) -> InteractionCSR:
 # keyed by object identity, a few entries, oldest evicted first
 _cache_keep: dict[tuple[int, str], tuple[Any, Any]] = {}
 _CACHE_LIMIT = 8
+# The cached plans / scorer states carry mutable device state (status word, work counter, Σ‖Δ‖²,
+# contribution pool): calls into this mirror are serialised per process.  The reference's score_*
+# are re-entrant on CPU threads; here concurrent callers queue on the one GPU stream anyway.
+_engine_lock = threading.RLock()
 
 
 def _cached(obj: Any, tag: str, make: Callable[[], Any]) -> Any:
     key = (id(obj), tag)
-    ent = _cache_keep.get(key)
-    if ent is not None and ent[0] is obj:
-        return ent[1]
-    val = make()
-    if len(_cache_keep) >= _CACHE_LIMIT:
-        _cache_keep.pop(next(iter(_cache_keep)))
-    _cache_keep[key] = (obj, val)
-    return val
+    with _engine_lock:
+        ent = _cache_keep.get(key)
+        if ent is not None and ent[0] is obj:
+            return ent[1]
+        val = make()
+        if len(_cache_keep) >= _CACHE_LIMIT:
+            _cache_keep.pop(next(iter(_cache_keep)))
+        _cache_keep[key] = (obj, val)
+        return val
 
 
 def clear_cache() -> None:
@@ -160,6 +165,10 @@ def _als_task(mode: int, matrix: Any, this: np.ndarray, other: np.ndarray, otor,
             raise ValueError("otor must be k x k")
 
     def run(task: AccelTask) -> float:
+        with _engine_lock:
+            return run_locked(task)
+
+    def run_locked(task: AccelTask) -> float:
         dev = _lib.require_device()
         dm = _cached(matrix, "csr", lambda: engine.DeviceCSR.from_host(csr, dev))
         plan = _cached(matrix, f"plan{k}", lambda: engine.ALSHalfPlan.create(dm, k))
@@ -204,6 +213,10 @@ def compute_similarities(
         raise AssertionError("matrix shapes do not match `shape`")
 
     def run(task: AccelTask) -> list[InteractionCSR]:
+        with _engine_lock:
+            return run_locked(task)
+
+    def run_locked(task: AccelTask) -> list[InteractionCSR]:
         dev = _lib.require_device()
         d_ui = _cached(ui_ratings, "csr", lambda: engine.DeviceCSR.from_host(ui, dev))
         d_iu = _cached(iu_ratings, "csr", lambda: engine.DeviceCSR.from_host(iu, dev))
@@ -250,6 +263,7 @@ def _score(sims: Any, ref_items, ref_rates, tgt_items, max_nbrs: int, min_nbrs: 
     ti = _null_to_neg(tgt_items)
     rv = None if ref_rates is None else _to_f32(ref_rates)
     i64 = torch.int64
+    # (KnnScorerState.score holds the state's own lock around its mutable device scratch)
     scores, counts = st.score(
         torch.tensor([0, len(ri)], dtype=i64, device=dev),
         torch.from_numpy(ri).to(dev),

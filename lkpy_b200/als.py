@@ -22,7 +22,7 @@ from typing import Literal
 
 import numpy as np
 import torch
-from pydantic import AliasChoices, BaseModel, Field, PositiveFloat, PositiveInt
+from pydantic import AliasChoices, BaseModel, Field, PositiveFloat, PositiveInt, field_validator
 
 from . import _lib, engine
 from .components import Component, Dataset, ItemList, ModelTrainer, RecQuery, TrainingOptions, UsesTrainer
@@ -36,6 +36,14 @@ class ALSConfig(BaseModel):
     user_embeddings: bool | Literal["prefer"] = True
     gather_dtype: Literal["float32", "bfloat16"] = "float32"
     "Engine option: storage type of the gathered (opposite) factor rows."
+
+    @field_validator("embedding_size", mode="after")
+    @staticmethod
+    def check_embedding_size(k) -> int:
+        # engine limit (the reference has none), reported at configuration time
+        if k > engine.ALS_MAX_FEATURES:
+            raise ValueError(f"embedding_size={k} exceeds the engine limit of {engine.ALS_MAX_FEATURES}")
+        return k
 
     @property
     def user_reg(self) -> float:
@@ -488,6 +496,8 @@ class BiasedMFScorer(ALSBase):
         uoff = ratings - self.bias.global_bias
         uoff[inums >= 0] -= self.bias.item_biases[inums[inums >= 0]]
         u_bias = float(np.sum(uoff) / (np.sum(np.isfinite(uoff)) + self.bias.damping[0]))
+        if not np.isfinite(u_bias):  # BiasModel.compute_for_items zeroes a NaN user bias (basic/bias.py)
+            u_bias = 0.0
         biases = np.full(len(items), self.bias.global_bias, dtype=np.float32)
         biases[inums >= 0] += self.bias.item_biases[inums[inums >= 0]]
         rv = (ratings - biases - u_bias)[mask].astype(np.float32)

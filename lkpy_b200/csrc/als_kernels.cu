@@ -447,8 +447,7 @@ __global__ void otor_reduce_kernel(const float *__restrict__ partial, int nblock
     }
 }
 
-int launch_als_tc(const lk_als_args &a, cudaStream_t st);   // als_tc.cu  (tensor-core Gram, shared-memory solve)
-int launch_als_tcr(const lk_als_args &a, cudaStream_t st);  // als_tcr.cu (tensor-core Gram, register solve)
+int launch_als_tc(const lk_als_args &a, cudaStream_t st);  // als_tc.cu (tensor-core Gram + in-TMEM solve)
 
 static int pad_features(int k) { return k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : -1; }
 
@@ -587,15 +586,13 @@ int lk_als_half_epoch(const lk_als_args *args, void *stream)
     LK_CUDA_TRY(cudaMemsetAsync(a.d_work_counter, 0, sizeof(int32_t), st));
     if (a.n_split_rows > 0)
         LK_CUDA_TRY(cudaMemsetAsync(a.d_split_counters, 0, sizeof(int32_t) * a.n_split_rows, st));
-    if (a.other_dtype == LK_DTYPE_F32) return dispatch_k<float>(a, st);
-    // k = 64, bf16 rows, unweighted / uniformly weighted Gram: tensor-core kernel (als_tc.cu)
-    // LK_ALS_TC selects the kernel for diagnostics: 0 = SIMT, 2 = the register-solve variant
-    // (als_tcr.cu, measured slower in round 1), anything else / unset = als_tc.cu.
-    const char *sel = getenv("LK_ALS_TC");
-    if (!(sel && sel[0] == '0')) {
-        const int rc = (sel && sel[0] == '2') ? launch_als_tcr(a, st) : launch_als_tc(a, st);
+    // k = 64: tensor-core kernel (als_tc.cu) unless switched off (option LK_ALS_TC = 0) or the
+    // configuration is outside what it covers (returns 1: fall through to the SIMT kernel)
+    if (options().als_tc != 0) {
+        const int rc = launch_als_tc(a, st);
         if (rc <= 0) return rc;
     }
+    if (a.other_dtype == LK_DTYPE_F32) return dispatch_k<float>(a, st);
     return dispatch_k<__nv_bfloat16>(a, st);
 }
 

@@ -694,18 +694,18 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
     if (a.k != tc::KP || a.other_dtype != LK_DTYPE_BF16) return 1;
     if (a.mode == LK_ALS_IMPLICIT && !a.vals_uniform) return 1;
     if (reinterpret_cast<uintptr_t>(a.d_other) % 16 != 0) return 1;
-    int interleave = 1;
-    if (const char *e = getenv("LK_ALS_TC_INTERLEAVE")) interleave = e[0] != '0';
+    const Options &opt = options();
+    const int interleave = opt.als_tc_interleave != 0;
     const int cols = interleave ? tc::TMEM_COLS : 2 * tc::TMEM_COLS;
     const int smem = tc::SMEM_BYTES;
     int64_t groups = (a.n_chunks + tc::WARPS - 1) / tc::WARPS;
     // 3 CTAs per SM by shared memory (73 KB) and registers; TMEM allows 512 / cols.  (The occupancy
     // API returned 1 for the user-half launch on the B200 box, so the design figure is used.)
     int occ = 3;
-    if (const char *e = getenv("LK_ALS_TC_OCC")) occ = std::max(1, std::min(3, atoi(e)));  // diagnostics
+    if (opt.als_tc_occ > 0) occ = std::max(1, std::min(3, opt.als_tc_occ));  // diagnostics
     // LK_ALS_TCS=0 keeps the per-warp shared-memory solve (diagnostics); default: tensor-core solve
-    bool tcs = interleave != 0;
-    if (const char *e = getenv("LK_ALS_TCS")) tcs = tcs && e[0] != '0';
+    const bool tcs_opt = interleave != 0 && opt.als_tcs != 0;
+    bool tcs = tcs_opt;
     // the tensor-core path solves (A / v) x = y / v: not for a zero confidence weight
     if (a.mode == LK_ALS_IMPLICIT && !(fabsf(a.uniform_val) > 1e-20f)) tcs = false;
     occ = std::max(1, std::min(occ, 512 / (cols + tc::TMEM_Y_COLS)));
@@ -716,8 +716,7 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
         return LK_OK;
     };
     // LK_ALS_GJ=1: block Gauss-Jordan instead of blocked Cholesky + block back substitution (experiment)
-    bool gj = false;
-    if (const char *e = getenv("LK_ALS_GJ")) gj = e[0] != '0';
+    const bool gj = opt.als_gj != 0;
     int rc;
     if (a.mode == LK_ALS_IMPLICIT)
         rc = !tcs  ? launch(als_tc_kernel<LK_ALS_IMPLICIT, false>)

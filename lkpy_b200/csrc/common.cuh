@@ -34,6 +34,21 @@ void set_error(const char *fmt, ...);
 
 int sm_count();
 
+// Diagnostic switches (capi.cu): defaults, overridden once from the LK_* environment variables at
+// first use and afterwards only through lk_set_option.  -1 = "not set, use the built-in choice".
+struct Options {
+    int als_tc = 1;             // 0: SIMT ALS kernel even where the tensor-core kernel applies
+    int als_tc_interleave = 1;  // 0: one accumulator per 64 TMEM columns (shared-memory solve only)
+    int als_tc_occ = -1;        // cap on resident CTAs per SM of the tensor-core kernel
+    int als_tcs = 1;            // 0: drain the systems to shared memory, one warp per solve
+    int als_gj = 0;             // 1: block Gauss-Jordan variant of the tensor-core solve
+    int als_tf32 = 1;           // 0: fp32 / non-uniformly weighted rows stay on the SIMT kernel
+    int knn_warps = -1;         // warps per CTA of the kNN build (8, 16, 32)
+    int knn_ctas = -1;          // resident CTAs per SM of the kNN build
+    int knn_score_seq = 0;      // 1: sequential scoring kernel even with a contribution pool
+};
+Options &options();
+
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------

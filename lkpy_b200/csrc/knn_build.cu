@@ -537,8 +537,8 @@ int lk_knn_geometry(int32_t n_users, int32_t n_items, lk_knn_geom *geom)
     LK_REQUIRE(geom != nullptr && n_users >= 0 && n_items >= 1, LK_ERR_INVALID,
                "lk_knn_geometry: bad arguments");
     int warps = 16, ctas = 2;
-    if (const char *e = getenv("LK_KNN_WARPS")) warps = atoi(e);
-    if (const char *e = getenv("LK_KNN_CTAS")) ctas = atoi(e);
+    if (options().knn_warps > 0) warps = options().knn_warps;
+    if (options().knn_ctas > 0) ctas = options().knn_ctas;
     LK_REQUIRE(warps == 8 || warps == 16 || warps == 32, LK_ERR_INVALID, "LK_KNN_WARPS must be 8, 16 or 32");
     LK_REQUIRE(ctas >= 1 && ctas <= 8, LK_ERR_INVALID, "LK_KNN_CTAS must be 1..8");
     // shared memory budget per CTA (227 KB usable per SM, 1 KB reserved per CTA)

@@ -21,6 +21,8 @@
 // position in the query's target list, so cost is proportional to the
 // contributions and the target list, never to n_items.
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace lk {
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
 {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gwarp >= a.slotmap_warps) return;  // one slot-map row per working warp
     int32_t *slotmap = a.d_slotmap + (size_t)gwarp * a.n_items;
     const bool explicit_fb = a.d_ref_vals != nullptr;
     const float qnan = __int_as_float(0x7fc00000);
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args 
 {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gwarp >= a.slotmap_warps) return;  // one slot-map row per working warp
     int32_t *slotmap = a.d_slotmap + (size_t)gwarp * a.n_items;
     const bool explicit_fb = a.d_ref_vals != nullptr;
     const float qnan = __int_as_float(0x7fc00000);
@@ -537,14 +541,15 @@ int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
                    a.d_tgt_indptr && a.d_tgt_items && a.d_slotmap && a.d_acc_ws && a.d_acc_tw &&
                    a.d_acc_cnt && a.d_scores && a.d_counts && a.d_work_counter && a.d_status,
                LK_ERR_INVALID, "lk_knn_score_batch: null pointer");
-    LK_REQUIRE(a.slotmap_warps >= lk_knn_score_warps(), LK_ERR_INVALID, "slotmap too small");
+    LK_REQUIRE(a.slotmap_warps >= 1, LK_ERR_INVALID, "slotmap too small");
     if (a.n_queries == 0) return LK_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LK_CUDA_TRY(cudaMemsetAsync(a.d_work_counter, 0, sizeof(int32_t), st));
-    const int blocks = sm_count() * SCORE_WARPS_PER_SM / 8;
+    // as many warps as there are slot-map rows (the caller sizes them to the batch), at most the full grid
+    const int64_t warps = std::min<int64_t>(a.slotmap_warps, lk_knn_score_warps());
+    const int blocks = (int)((warps + 7) / 8);
     // with a contribution pool the list-based kernel runs (LK_KNN_SCORE_SEQ=1 forces the sequential one)
-    const char *seq = getenv("LK_KNN_SCORE_SEQ");
-    if (a.d_pool != nullptr && a.d_pool_cursor != nullptr && !(seq && seq[0] == '1')) {
+    if (a.d_pool != nullptr && a.d_pool_cursor != nullptr && options().knn_score_seq != 1) {
         LK_REQUIRE(reinterpret_cast<uintptr_t>(a.d_pool) % 16 == 0 && a.pool_entries >= 0, LK_ERR_INVALID,
                    "lk_knn_score_batch: bad contribution pool");
         LK_CUDA_TRY(cudaMemsetAsync(a.d_pool_cursor, 0, sizeof(unsigned long long), st));

@@ -199,6 +199,10 @@ def knn_item_matrices(
         means = np.zeros(sums.shape, dtype=np.float32)
         np.divide(sums, counts, out=means, where=counts > 0)
         rmat.data = rmat.data - np.repeat(means, counts)
+        if np.allclose(rmat.data, 0.0):  # checked on the centred values, before normalisation (knn/item.py:211-216)
+            import warnings
+
+            warnings.warn("Ratings seem to have the same value, centering is not recommended.", UserWarning)
     norms = spla.norm(rmat, 2, axis=0)
     cmat = rmat / np.maximum(norms, np.finfo("f4").smallest_normal)
     cmat = cmat.astype(np.float32)

@@ -9,6 +9,7 @@ PyTorch is used for device memory, streams and (in ``lkpy_b200.parallel``)
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -19,6 +20,10 @@ from ._lib import LkAlsArgs, LkKnnBuildArgs, LkKnnGeom, LkKnnScoreArgs, check, l
 from .data import InteractionCSR
 
 DEFAULT_CHUNK_NNZ = 4096
+#: engine limits the reference does not have: validated up front by the configs
+ALS_MAX_FEATURES = 128
+KNN_SCORE_MAX_NBRS = 128
+KNN_MERGE_SMEM_LIMIT = 200 * 1024  # n_halves * save_nbrs * 16 B must fit (lk_knn_merge_topk)
 #: optional int64[8] device tensor receiving per-phase cycle counters of the ALS kernels (diagnostics)
 PROF_BUFFER = None
 
@@ -286,6 +291,11 @@ class KnnBuildPlan:
         L = lib()
         dev = self.ui.indptr.device
         n_items, H, K = self.geom.n_items, self.geom.n_halves, int(save_nbrs)
+        if H * K * 16 > KNN_MERGE_SMEM_LIMIT:  # checked before the build runs, not after it
+            raise _lib.EngineError(
+                f"save_nbrs={K} with {H} column blocks exceeds the merge limit "
+                f"(n_halves * save_nbrs <= {KNN_MERGE_SMEM_LIMIT // 16}); use save_nbrs=None"
+            )
         order = self.order if order is None else order.to(torch.int32).contiguous()
         ws = self.extra.get(("topk", K))
         if ws is None:  # workspaces are allocated once per plan and K, reused by every build
@@ -367,26 +377,38 @@ def topk_rows_to_csr(
 
 @dataclass
 class KnnScorerState:
-    """Similarity matrix in HBM plus the per-warp slot maps."""
+    """Similarity matrix in HBM; per-warp slot maps and scratch are sized to the batches actually scored."""
 
     n_items: int
     sim_indptr: torch.Tensor  # int64
     sim_cols: torch.Tensor
     sim_vals: torch.Tensor
-    slotmap: torch.Tensor
-    slotmap_warps: int
+    max_warps: int
     work_counter: torch.Tensor
     status: torch.Tensor
-    heap_scratch: dict = field(default_factory=dict)  # max_nbrs -> per-warp heap states (allocated on first use)
+    slotmap: torch.Tensor | None = None  # [warps, n_items] int32, all -1 between calls; grown on demand
+    heap_scratch: dict = field(default_factory=dict)  # (max_nbrs, warps) -> per-warp heap states
+    lock: object = field(default_factory=threading.Lock)  # the mutable device state above is per-state
     HEAP_TARGETS_PER_WARP = 2048
     USE_LISTS = True  # list-based kernel (parallel over the history); False: the sequential kernel
 
-    def _heap(self, max_nbrs: int) -> tuple[torch.Tensor, int]:
+    def _slotmap(self, n_queries: int) -> tuple[torch.Tensor, int]:
+        """One slot-map row per working warp: min(n_queries, full grid) rows (a single query takes
+        n_items * 4 B, not grid * n_items * 4 B)."""
+        warps = max(1, min(int(n_queries), self.max_warps))
+        if self.slotmap is None or self.slotmap.shape[0] < warps:
+            self.slotmap = None
+            self.slotmap = torch.full((warps, self.n_items), -1, dtype=torch.int32, device=self.sim_cols.device)
+        return self.slotmap, int(self.slotmap.shape[0])
+
+    def _heap(self, max_nbrs: int, warps: int) -> tuple[torch.Tensor, int]:
+        """Heap states of the sequential kernel (only allocated when that kernel will run)."""
         per_warp = self.HEAP_TARGETS_PER_WARP * (2 + 2 * (int(max_nbrs) + 1))
-        t = self.heap_scratch.get(int(max_nbrs))
-        if t is None:
-            t = torch.empty(self.slotmap_warps * per_warp, dtype=torch.float32, device=self.sim_cols.device)
-            self.heap_scratch[int(max_nbrs)] = t
+        key = int(max_nbrs)
+        t = self.heap_scratch.get(key)
+        if t is None or t.numel() < warps * per_warp:
+            t = torch.empty(warps * per_warp, dtype=torch.float32, device=self.sim_cols.device)
+            self.heap_scratch[key] = t
         return t, per_warp
 
     @classmethod
@@ -403,7 +425,6 @@ class KnnScorerState:
             dev(indptr, torch.int64),
             dev(cols, torch.int32),
             dev(vals, torch.float32),
-            torch.full((warps * n_items,), -1, dtype=torch.int32, device=device),
             warps,
             torch.zeros(1, dtype=torch.int32, device=device),
             torch.zeros(1, dtype=torch.int32, device=device),
@@ -420,6 +441,12 @@ class KnnScorerState:
         min_nbrs: int,
     ) -> tuple[torch.Tensor, torch.Tensor]:
         """Score a batch of queries; returns (scores with NaN nulls, counts with -1 nulls)."""
+        if not 1 <= int(max_nbrs) <= KNN_SCORE_MAX_NBRS:
+            raise ValueError(f"max_nbrs must be in 1..{KNN_SCORE_MAX_NBRS}")
+        with self.lock:  # status word, work counter, pool and slot maps are shared by the callers of one state
+            return self._score_locked(ref_indptr, ref_items, ref_vals, tgt_indptr, tgt_items, max_nbrs, min_nbrs)
+
+    def _score_locked(self, ref_indptr, ref_items, ref_vals, tgt_indptr, tgt_items, max_nbrs, min_nbrs):
         dev = self.sim_cols.device
         nq = ref_indptr.numel() - 1
         nt = tgt_items.numel()
@@ -429,6 +456,7 @@ class KnnScorerState:
         acc_tw = torch.empty(max(nt, 1), dtype=torch.float32, device=dev)
         acc_cnt = torch.empty(max(nt, 1), dtype=torch.int32, device=dev)
         self.status.zero_()
+        slotmap, warps = self._slotmap(nq)
         a = LkKnnScoreArgs()
         a.n_items = self.n_items
         a.d_sim_indptr, a.d_sim_cols, a.d_sim_vals = ptr(self.sim_indptr), ptr(self.sim_cols), ptr(self.sim_vals)
@@ -436,13 +464,12 @@ class KnnScorerState:
         a.d_ref_indptr, a.d_ref_items, a.d_ref_vals = ptr(ref_indptr), ptr(ref_items), ptr(ref_vals)
         a.d_tgt_indptr, a.d_tgt_items = ptr(tgt_indptr), ptr(tgt_items)
         a.max_nbrs, a.min_nbrs = int(max_nbrs), int(min_nbrs)
-        a.d_slotmap, a.slotmap_warps = ptr(self.slotmap), self.slotmap_warps
+        a.d_slotmap, a.slotmap_warps = ptr(slotmap), warps
         a.d_acc_ws, a.d_acc_tw, a.d_acc_cnt = ptr(acc_ws), ptr(acc_tw), ptr(acc_cnt)
         a.d_scores, a.d_counts = ptr(scores), ptr(counts)
         a.d_work_counter, a.d_status = ptr(self.work_counter), ptr(self.status)
-        heap, per_warp = self._heap(max_nbrs)
-        a.d_heap_scratch, a.heap_floats_per_warp = ptr(heap), per_warp
-        if self.USE_LISTS and ref_items.numel() > 0:
+        use_lists = self.USE_LISTS and ref_items.numel() > 0 and _lib.get_option("LK_KNN_SCORE_SEQ") != 1
+        if use_lists:
             # contribution pool for the list-based kernel: one 16-byte entry per (reference item,
             # similarity-row entry) pair of the batch
             r = ref_items.long()
@@ -456,6 +483,10 @@ class KnnScorerState:
                 self.heap_scratch["pool_cursor"] = torch.zeros(1, dtype=torch.int64, device=dev)
             a.d_pool, a.pool_entries = ptr(pool), pool.numel() // 4
             a.d_pool_cursor = ptr(self.heap_scratch["pool_cursor"])
+        else:
+            # the sequential kernel is the one that reads the per-warp heap states
+            heap, per_warp = self._heap(max_nbrs, warps)
+            a.d_heap_scratch, a.heap_floats_per_warp = ptr(heap), per_warp
         check(lib().lk_knn_score_batch(C.byref(a), stream_ptr()), "lk_knn_score_batch")
         # keep scratch alive until the stream has consumed it
         torch.cuda.current_stream().synchronize()

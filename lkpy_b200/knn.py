@@ -12,7 +12,6 @@ one query per call on one thread).
 
 from __future__ import annotations
 
-import warnings
 from typing import Literal
 
 import numpy as np
@@ -38,6 +37,15 @@ class ItemKNNConfig(BaseModel, extra="forbid"):
     def clamp_min_sim(sim) -> float:
         return max(sim, float(np.finfo(np.float64).smallest_normal))
 
+    @field_validator("max_nbrs", mode="after")
+    @staticmethod
+    def check_max_nbrs(n) -> int:
+        # engine limit (the reference has none): a target's accumulator heap lives in thread-local
+        # memory of the scoring kernel — reported here, not at the first scoring call
+        if n > engine.KNN_SCORE_MAX_NBRS:
+            raise ValueError(f"max_nbrs={n} exceeds the engine limit of {engine.KNN_SCORE_MAX_NBRS}")
+        return n
+
     @property
     def explicit(self) -> bool:
         return self.feedback == "explicit"
@@ -62,8 +70,6 @@ class ItemKNNScorer(Component, Trainable):
         dev = _lib.require_device()
         # host prep exactly as knn/item.py:141-157,202-228 (bitwise-identical f32 inputs)
         ui, iu, means = knn_item_matrices(ds.interactions, self.config.explicit)
-        if means is not None and np.allclose(ui.values, 0.0):
-            warnings.warn("Ratings seem to have the same value, centering is not recommended.", UserWarning)
         plan = engine.KnnBuildPlan.create(engine.DeviceCSR.from_host(ui, dev), engine.DeviceCSR.from_host(iu, dev))
         if self.config.save_nbrs:
             cols, vals, cnt = plan.build_topk(self.config.min_sim, int(self.config.save_nbrs))

@@ -44,3 +44,21 @@ def cuda_lib():
 
     _build.build()
     return _lib.lib()
+
+
+@pytest.fixture
+def lk_options(cuda_lib):
+    """Set diagnostic kernel switches through ``lk_set_option`` (the LK_* environment is read once, at
+    load); every switch touched is restored when the test ends."""
+    from lkpy_b200 import _lib
+
+    saved: dict[str, int] = {}
+
+    def set_(name: str, value: int) -> None:
+        if name not in saved:
+            saved[name] = _lib.get_option(name)
+        _lib.set_option(name, value)
+
+    yield set_
+    for name, value in saved.items():
+        _lib.set_option(name, value)

@@ -16,21 +16,19 @@ from helpers import rel_fro, small_synth
 
 pytestmark = pytest.mark.gpu
 
-# solve variants of the tensor-core kernel (environment switches read by launch_als_tc / dispatch)
+# solve variants of the tensor-core kernel (switches of lk_set_option, read by launch_als_tc / dispatch)
 VARIANTS = {
     "tc-cholesky": {},  # default: blocked Cholesky with tcgen05 trailing updates (chol_tc.cuh)
-    "tc-gauss-jordan": {"LK_ALS_GJ": "1"},  # block Gauss-Jordan variant of the same
-    "smem-solve": {"LK_ALS_TCS": "0"},  # systems drained to shared memory, one warp per solve
-    "smem-solve-wide": {"LK_ALS_TCS": "0", "LK_ALS_TC_INTERLEAVE": "0"},  # one accumulator per 64 columns
-    "register-solve": {"LK_ALS_TC": "2"},  # als_tcr.cu experiment
+    "tc-gauss-jordan": {"LK_ALS_GJ": 1},  # block Gauss-Jordan variant of the same
+    "smem-solve": {"LK_ALS_TCS": 0},  # systems drained to shared memory, one warp per solve
+    "smem-solve-wide": {"LK_ALS_TCS": 0, "LK_ALS_TC_INTERLEAVE": 0},  # one accumulator per 64 columns
 }
+DEFAULTS = {"LK_ALS_TC": 1, "LK_ALS_TCS": 1, "LK_ALS_GJ": 0, "LK_ALS_TC_INTERLEAVE": 1}
 
 
-def _set(monkeypatch, variant):
-    for key in ("LK_ALS_TC", "LK_ALS_TCS", "LK_ALS_GJ", "LK_ALS_TC_INTERLEAVE"):
-        monkeypatch.delenv(key, raising=False)
-    for key, val in VARIANTS[variant].items():
-        monkeypatch.setenv(key, val)
+def _set(lk_options, variant):
+    for key, val in {**DEFAULTS, **VARIANTS[variant]}.items():
+        lk_options(key, val)
 
 
 def _run(mode, csr, this, other, reg, chunk_nnz=engine.DEFAULT_CHUNK_NNZ):
@@ -59,8 +57,8 @@ def _oracle(mode, csr, this, other, reg):
 
 @pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("mode", ["implicit", "explicit"])
-def test_tc_kernel_parity(cuda_lib, monkeypatch, mode, variant):
-    _set(monkeypatch, variant)
+def test_tc_kernel_parity(cuda_lib, lk_options, mode, variant):
+    _set(lk_options, variant)
     inter = small_synth(900, 500, 40000, seed=21)
     rng = np.random.default_rng(21)
     k = 64
@@ -80,16 +78,16 @@ def test_tc_kernel_parity(cuda_lib, monkeypatch, mode, variant):
         empty = np.diff(csr.indptr) == 0
         assert np.all(got[empty] == 0.0)
         # the SIMT kernel on the same inputs agrees to rounding
-        monkeypatch.setenv("LK_ALS_TC", "0")
+        lk_options("LK_ALS_TC", 0)
         simt, _, _ = _run(mode, csr, this, other, 0.1)
-        _set(monkeypatch, variant)
+        _set(lk_options, variant)
         assert rel_fro(got, simt) < 2e-5
 
 
-@pytest.mark.parametrize("variant", ["tc-cholesky", "tc-gauss-jordan", "smem-solve", "register-solve"])
+@pytest.mark.parametrize("variant", ["tc-cholesky", "tc-gauss-jordan", "smem-solve"])
 @pytest.mark.parametrize("mode", ["implicit", "explicit"])
-def test_tc_split_rows_deterministic(cuda_lib, monkeypatch, variant, mode):
-    _set(monkeypatch, variant)
+def test_tc_split_rows_deterministic(cuda_lib, lk_options, variant, mode):
+    _set(lk_options, variant)
     inter = small_synth(300, 200, 20000, seed=5)
     rng = np.random.default_rng(5)
     if mode == "implicit":
@@ -110,10 +108,10 @@ def test_tc_split_rows_deterministic(cuda_lib, monkeypatch, variant, mode):
 
 
 @pytest.mark.parametrize("variant", ["tc-cholesky", "tc-gauss-jordan"])
-def test_tc_solve_badly_conditioned(cuda_lib, monkeypatch, variant):
+def test_tc_solve_badly_conditioned(cuda_lib, lk_options, variant):
     """Large Gram, small ridge (cond ~1e4): the tensor-core solve stays within a small factor of what
     f32 arithmetic can deliver (the f32 oracle's own distance to the f64 oracle)."""
-    _set(monkeypatch, variant)
+    _set(lk_options, variant)
     inter = small_synth(400, 300, 60000, seed=9)
     ui, _ = data.als_implicit_matrices(inter, 40.0)
     rng = np.random.default_rng(9)
@@ -128,9 +126,9 @@ def test_tc_solve_badly_conditioned(cuda_lib, monkeypatch, variant):
     assert e_gpu < max(1e-4, 3.0 * e_cpu), (e_gpu, e_cpu)
 
 
-def test_tc_zero_weight_falls_back(cuda_lib, monkeypatch):
+def test_tc_zero_weight_falls_back(cuda_lib, lk_options):
     """weight = 0 makes every confidence 0: (A / v) is undefined, the shared-memory solve takes over."""
-    _set(monkeypatch, "tc-cholesky")
+    _set(lk_options, "tc-cholesky")
     inter = small_synth(200, 150, 5000, seed=3)
     ui, _ = data.als_implicit_matrices(inter, 0.0)
     rng = np.random.default_rng(3)
@@ -142,9 +140,9 @@ def test_tc_zero_weight_falls_back(cuda_lib, monkeypatch):
     assert rel_fro(got, ref) < 1e-4
 
 
-def test_tc_non_uniform_weights_fall_back(cuda_lib, monkeypatch):
+def test_tc_non_uniform_weights_fall_back(cuda_lib, lk_options):
     """use_ratings=True confidences are not uniform: the SIMT kernel must take the launch."""
-    _set(monkeypatch, "tc-cholesky")
+    _set(lk_options, "tc-cholesky")
     inter = small_synth(400, 300, 15000, seed=8)
     ui, _ = data.als_implicit_matrices(inter, 40.0, use_ratings=True)
     rng = np.random.default_rng(8)
@@ -157,10 +155,10 @@ def test_tc_non_uniform_weights_fall_back(cuda_lib, monkeypatch):
 
 
 @pytest.mark.parametrize("variant", ["tc-cholesky", "tc-gauss-jordan", "smem-solve"])
-def test_tc_not_positive_definite_is_reported(cuda_lib, monkeypatch, variant):
+def test_tc_not_positive_definite_is_reported(cuda_lib, lk_options, variant):
     """A system that is not positive definite (the reference's `ALS solve error`, implicit.rs:79) sets the
     status word and leaves the row untouched — also on the tensor-core path."""
-    _set(monkeypatch, variant)
+    _set(lk_options, variant)
     inter = small_synth(60, 40, 600, seed=2)
     ui, _ = data.als_implicit_matrices(inter, 40.0)
     dev = _lib.require_device()

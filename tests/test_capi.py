@@ -90,16 +90,17 @@ def test_als_plan_covers_every_nonzero_once(cuda_lib, chunk):
         _lib.check(cuda_lib.lk_als_plan_size(hp.ctypes.data, iu.shape[0], 8, C.byref(nc), C.byref(ns), C.byref(nslot)))
 
 
-def test_knn_geometry(cuda_lib, monkeypatch):
+def test_knn_geometry(cuda_lib, lk_options):
     g = _lib.LkKnnGeom()
     for n_items in (4, 9066, 59047, 500_000):
         _lib.check(cuda_lib.lk_knn_geometry(1000, n_items, C.byref(g)))
         assert g.warps * g.tile_cols * g.n_halves >= n_items
         assert g.tile_cols % 32 == 0 and g.n_subtiles == g.n_halves * g.warps
         assert g.smem_bytes * g.ctas_per_sm <= 227 * 1024
-    monkeypatch.setenv("LK_KNN_WARPS", "7")
+    lk_options("LK_KNN_WARPS", 7)
     assert cuda_lib.lk_knn_geometry(10, 10, C.byref(g)) == _lib.LK_OK - 1
     assert b"LK_KNN_WARPS" in cuda_lib.lk_last_error()
+    assert cuda_lib.lk_set_option(b"LK_NO_SUCH_SWITCH", 1) != _lib.LK_OK
 
 
 def test_component_configs():

@@ -63,10 +63,10 @@ def test_build_toy(cuda_lib):
 
 
 @pytest.mark.parametrize("ctas,warps", [("8", "8"), ("4", "16"), ("1", "32")])
-def test_build_multi_half_geometry(cuda_lib, ml_small, ctas, warps, monkeypatch):
+def test_build_multi_half_geometry(cuda_lib, ml_small, ctas, warps, lk_options):
     """Small shared-memory budgets force several column halves and the merge path."""
-    monkeypatch.setenv("LK_KNN_CTAS", ctas)
-    monkeypatch.setenv("LK_KNN_WARPS", warps)
+    lk_options("LK_KNN_CTAS", int(ctas))
+    lk_options("LK_KNN_WARPS", int(warps))
     ui, iu, _ = data.knn_item_matrices(ml_small, False)  # implicit: 76% of rows tie at K=20
     ref = oracle.knn_build(ui, iu, 1e-6, 20)
     got, plan = _build(ui, iu, 1e-6, 20)

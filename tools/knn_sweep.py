@@ -19,7 +19,8 @@ d_ui = engine.DeviceCSR.from_host(kui, dev)
 d_iu = engine.DeviceCSR.from_host(kiu, dev)
 combos = [c.split(":") for c in (sys.argv[1] if len(sys.argv) > 1 else "16:2,8:2,8:3,16:1,32:1,8:4").split(",")]
 for warps, ctas in combos:
-    os.environ["LK_KNN_WARPS"], os.environ["LK_KNN_CTAS"] = warps, ctas
+    _lib.set_option("LK_KNN_WARPS", int(warps))
+    _lib.set_option("LK_KNN_CTAS", int(ctas))
     plan = engine.KnnBuildPlan.create(d_ui, d_iu)
     for rep in range(2):
         torch.cuda.synchronize()
