@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """
-bench.py — ALS-implicit epoch time and item-kNN build throughput on
-ML-25M-shaped synthetic interactions (BASELINE.json metric / configs[1], [2]).
+bench.py — ALS-implicit epoch time and item-kNN build / score throughput on
+ML-25M-shaped synthetic interactions (BASELINE.json metric; configs[1], configs[2]) and the two
+scale-out configurations (configs[3], configs[4]).
 
-    python bench.py --gpus 1 --steps 5 --warmup 3
+    python bench.py --gpus 1 --steps 20 --warmup 3                 # the default line (configs[1] + [2])
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # CPU restatement of the reference path
+    python bench.py --impl reference ...                            # CPU restatement of the reference path
+    ... bench.py --gpus 8 --workload als100m                        # configs[3]: 100 M interactions, k=128
+    ... bench.py --gpus 8 --workload knn1b                          # configs[4]: 1 B interactions, kNN build
 
-One JSON line on stdout (rank 0).  A "step" is one ALS epoch (user half-epoch +
-item half-epoch, each = OtOr kernel + row-solve kernel, + the factor all-gather
-when N > 1) over the resident CSR matrices.  `value` is the epoch time with
-everything resident in HBM; `e2e` is the same epoch through the public trainer
-API with the factor tables coming from / going back to pinned host memory inside
-the timed region.  Riding along: "als_fp32" (the same epoch with fp32 gathered rows),
-"knn" (item-kNN build items/s with its kernel roofline and CPU figure, batched
-scoring users/s) and, at N=1, "recommend" (batched scoring + top-100 users/s with
-the selection kernel's roofline and the per-query CPU figure).  "cpu_baseline" and
-`--impl reference` time the CPU restatement of the reference path (oracle/) on a
-bounded sample at its best thread count.  Only the JSON line goes to stdout.
+One JSON line on stdout (rank 0).  A "step" is one ALS epoch (user half-epoch + item half-epoch,
+each = OtOr kernel + row-solve kernel, + the factor exchange when N > 1) over the resident CSR
+matrices.  `value` is the epoch time with everything resident in HBM; `e2e` is the same epoch
+through the public trainer API with the factor tables coming from / going back to pinned host
+memory inside the timed region.  Riding along in the same line:
+  "als_fp32"   the same epoch with fp32 gathered rows (the like-for-like figure against the f32 reference),
+  "knn"        item-kNN build items/s (kernel roofline, CPU baseline, e2e through the plugin call
+               `accel.compute_similarities` with host CSR in / host CSR out, and through
+               `ItemKNNScorer.train`), batched scoring of ALL users against all items (users/s, roofline),
+  "recommend"  (N=1) batched ALS scoring + top-100 users/s,
+  "parity"     oracle checks at THIS shape, run after the timed loops: sampled rows of one ALS
+               half-step (bf16 and fp32 rows; split / empty / short rows included) against the f64 oracle,
+               sampled item-kNN rows bit-exact against the oracle, and at N > 1 cross-rank equality of
+               the replicas + equality with a single-GPU half-step.  A mismatch makes the run exit 1.
+"cpu_baseline" and `--impl reference` time the CPU restatement of the reference path (oracle/) on a
+bounded sample: median of 3 repeats, thread sweep including the reference's default of 8 threads.
+Only the JSON line goes to stdout.
 """
 
 from __future__ import annotations
@@ -44,6 +53,7 @@ WEIGHT = 40.0
 REG = 0.1
 KNN_SAVE = 20
 KNN_MIN_SIM = 1e-6
+KNN_MAX_NBRS = 20
 
 
 def log(*a):
@@ -66,7 +76,7 @@ class ClockSampler:
     )
 
     def __init__(self, gpu_index: int = 0):
-        self.rows: list[list[str]] = []
+        self.rows: list = []
         self.proc = None
         self.gpu = gpu_index
 
@@ -148,6 +158,11 @@ def knn_build_bytes(products: int, nnz: int, n_users: int, n_items: int, nnz_out
     return float(8 * products + 8 * nnz + 4 * (n_items + n_users + 2) + 8 * nnz_out)
 
 
+def knn_score_bytes(sim_entries_touched: int, hist: int, targets: int) -> float:
+    """8·Σ_{r∈hist}|S.row(r)| + 8·|hist| + 8·|targets| (summed over the batch)."""
+    return float(8 * sim_entries_touched + 8 * hist + 8 * targets)
+
+
 def load_peaks() -> tuple[float, str]:
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -157,10 +172,13 @@ def load_peaks() -> tuple[float, str]:
 
 def ncu_traffic(key: str, world: int) -> float | None:
     """DRAM bytes per launch from the committed ncu --set full capture (N=1, default workload only)."""
-    f = ROOT / "profiles" / "r01_traffic.json"
-    if world != 1 or not f.exists():
-        return None
-    return float(json.loads(f.read_text()).get(key, 0)) or None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        f = ROOT / "profiles" / name
+        if world == 1 and f.exists():
+            v = json.loads(f.read_text()).get(key)
+            if v:
+                return float(v)
+    return None
 
 
 # ---------------------------------------------------------------------------
@@ -180,6 +198,11 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def thread_candidates(top: int) -> list[int]:
+    """All host threads, half of them, and 8 = the reference's default pool (schemas/settings.py:182-185)."""
+    return sorted({t for t in (top, max(top // 2, 1), 32, 8) if 1 <= t <= top}, reverse=True)
+
+
 def _slice_rows(csr, lo: int, hi: int):
     from lkpy_b200.data import InteractionCSR
 
@@ -189,83 +212,106 @@ def _slice_rows(csr, lo: int, hi: int):
     )
 
 
-def cpu_als_epoch_estimate(ui, iu, p, q, budget_s: float, threads: int) -> dict:
+def cpu_als_epoch_estimate(ui, iu, p, q, budget_s: float, threads: int, k: int = K) -> dict:
     """
-    Time the oracle (BLAS sgemm Gram + LAPACK sposv) on leading row ranges of both halves and
-    scale by nnz to a full epoch.  The thread count is the fastest of {all host threads the BLAS
-    allows, 32, 16, 8 (the reference's default, schemas/settings.py:183)} on a calibration slice:
-    on many-core hosts the row-parallel loop stops scaling well before all cores are busy.
+    The ALS half-epochs of the reference path on the host (oracle/lk_cpu_fast.c: thread-private
+    register-blocked Gram + vectorised Cholesky, scales with the cores) on leading row ranges of both
+    halves (rows are in random order with respect to length: user weights and the item permutation
+    are i.i.d.), scaled by nnz to a full epoch.  Per half: a calibration slice picks the sample
+    size for the budget, then every thread count in `thread_candidates` is timed three times on the
+    SAME sample and the median kept; the figure reported is the fastest thread count's median, the
+    8-thread figure (the reference's default pool) rides along.
     """
     import oracle
 
-    oracle.use_scipy_blas(True)
-    try:
-        out = {}
-        total = 0.0
-        parts = []
-        top = oracle.blas_threads(threads)
-        cands = sorted({t for t in (top, 32, 16, 8, 4) if t <= top}, reverse=True)
-        used = []
-        for name, csr, this, other in (("user", ui, p, q), ("item", iu, q, p)):
-            o32 = (other.T @ other + np.eye(K, dtype=np.float32) * REG).astype(np.float32)
-            # calibrate on ~3% of the nonzeros (thread count + rate), then size the sample to the budget
-            nnz = csr.nnz
-            rows_cal = max(int(np.searchsorted(csr.indptr, nnz // 20)), 16)
-            cal = _slice_rows(csr, 0, rows_cal)
-            best_t, t_cal = cands[0], float("inf")
-            for th in cands:
-                for _rep in range(2):  # best of two: the first call at a new thread count pays the pool start-up
-                    t0 = time.perf_counter()
-                    oracle.als_half("implicit", cal, this[:rows_cal], other, otor_mat=o32, threads=th)
-                    dt = time.perf_counter() - t0
-                    if dt < t_cal:
-                        best_t, t_cal = th, dt
-            used.append(best_t)
-            nnz_cal = int(csr.indptr[rows_cal])
-            want_nnz = int(min(nnz, nnz_cal * (budget_s / 2) / max(t_cal, 1e-6)))
-            rows = int(np.searchsorted(csr.indptr, want_nnz))
-            rows = min(max(rows, rows_cal), csr.shape[0])
-            t0 = time.perf_counter()
-            oracle.als_half("implicit", _slice_rows(csr, 0, rows), this[:rows], other, otor_mat=o32, threads=best_t)
-            t = time.perf_counter() - t0
-            nnz_s = int(csr.indptr[rows])
-            est = t * nnz / max(nnz_s, 1)
-            parts.append(f"{name} half: {rows} rows / {nnz_s} nnz in {t:.2f}s on {best_t} threads")
-            total += est
-        out["epoch_ms"] = total * 1e3
-        out["threads"] = max(used)
-        out["sample"] = "; ".join(parts) + f"; scaled by nnz to the full epoch; thread counts tried {cands}"
-        return out
-    finally:
-        oracle.use_scipy_blas(False)
+    total_best, total_8 = 0.0, 0.0
+    parts, per_threads = [], {}
+    cands = thread_candidates(threads)
+    best_threads = []
+    for name, csr, this, other in (("user", ui, p, q), ("item", iu, q, p)):
+        o32 = (other.T @ other + np.eye(k, dtype=np.float32) * REG).astype(np.float32)
+        nnz = csr.nnz
+        rows_cal = max(int(np.searchsorted(csr.indptr, nnz // 50)), 16)
+        cal = _slice_rows(csr, 0, rows_cal)
+        oracle.als_half_fast("implicit", cal, this[:rows_cal], other, otor_mat=o32, threads=cands[0])  # pool start-up
+        t0 = time.perf_counter()
+        oracle.als_half_fast("implicit", cal, this[:rows_cal], other, otor_mat=o32, threads=cands[0])
+        t_cal = time.perf_counter() - t0
+        nnz_cal = int(csr.indptr[rows_cal])
+        per_run = budget_s / 2 / (3 * len(cands))  # three repeats per thread count, two halves
+        want_nnz = int(min(nnz, nnz_cal * per_run / max(t_cal, 1e-6)))
+        rows = int(np.searchsorted(csr.indptr, want_nnz))
+        rows = min(max(rows, rows_cal), csr.shape[0])
+        sample = _slice_rows(csr, 0, rows)
+        nnz_s = int(csr.indptr[rows])
+        med = {}
+        for th in cands:
+            ts = []
+            for _rep in range(3):
+                t0 = time.perf_counter()
+                oracle.als_half_fast("implicit", sample, this[:rows], other, otor_mat=o32, threads=th)
+                ts.append(time.perf_counter() - t0)
+            med[th] = float(np.median(ts)) * nnz / max(nnz_s, 1)
+        bt = min(med, key=med.get)
+        best_threads.append(bt)
+        total_best += med[bt]
+        total_8 += med.get(8, med[min(med)])
+        for th, v in med.items():
+            per_threads[th] = per_threads.get(th, 0.0) + v * 1e3
+        parts.append(f"{name} half: rows 0..{rows} ({nnz_s} nnz = {nnz_s / nnz:.1%}), best at {bt} threads")
+    return {
+        "epoch_ms": total_best * 1e3,
+        "epoch_ms_8_threads": total_8 * 1e3,
+        "threads": max(best_threads),
+        "epoch_ms_by_threads": {str(t): round(v, 2) for t, v in sorted(per_threads.items())},
+        "sample": "; ".join(parts) + "; median of 3 per thread count, scaled by nnz to the full epoch",
+    }
 
 
 def cpu_knn_estimate(kui, kiu, cost: np.ndarray, budget_s: float, threads: int) -> dict:
+    """
+    Item-kNN build of the reference path on the host (oracle sim_row, thread-private accumulators)
+    on a FIXED stratified sample: items sorted by product count, every `stride`-th one taken, so the
+    sample carries the cost distribution of the whole matrix (hot items included in proportion);
+    median of 3 per thread count; scaled by product count.
+    """
     import oracle
 
     n_items = kiu.shape[0]
     total_cost = float(cost.sum())
-    rows_cal = max(64, n_items // 400)
+    order = np.argsort(-cost, kind="stable")
+    cands = thread_candidates(threads)
+    # calibrate on a 1/200 systematic sample
+    cal = order[100::200]
+    oracle.knn_build(kui, kiu, KNN_MIN_SIM, KNN_SAVE, row_list=cal, threads=cands[0])
     t0 = time.perf_counter()
-    oracle.knn_build(kui, kiu, KNN_MIN_SIM, KNN_SAVE, rows=(0, rows_cal), threads=threads)
+    oracle.knn_build(kui, kiu, KNN_MIN_SIM, KNN_SAVE, row_list=cal, threads=cands[0])
     t_cal = time.perf_counter() - t0
-    c_cal = float(cost[:rows_cal].sum())
-    want = c_cal * budget_s / max(t_cal, 1e-6)
-    rows = int(np.searchsorted(np.cumsum(cost), want))
-    rows = min(max(rows, rows_cal), n_items)
-    t0 = time.perf_counter()
-    oracle.knn_build(kui, kiu, KNN_MIN_SIM, KNN_SAVE, rows=(0, rows), threads=threads)
-    t = time.perf_counter() - t0
-    c = float(cost[:rows].sum())
-    est = t * total_cost / max(c, 1.0)
+    per_run = budget_s / (3 * len(cands))
+    frac = min(1.0, (float(cost[cal].sum()) / total_cost) * per_run / max(t_cal, 1e-6))
+    stride = max(1, int(round(1.0 / max(frac, 1e-9))))
+    sample = order[stride // 2 :: stride]
+    c = float(cost[sample].sum())
+    med = {}
+    for th in cands:
+        ts = []
+        for _rep in range(3):
+            t0 = time.perf_counter()
+            oracle.knn_build(kui, kiu, KNN_MIN_SIM, KNN_SAVE, row_list=sample, threads=th)
+            ts.append(time.perf_counter() - t0)
+        med[th] = float(np.median(ts)) * total_cost / max(c, 1.0)
+    bt = min(med, key=med.get)
     return {
-        "build_items_per_s": n_items / est,
-        "sample": f"items 0..{rows} ({c / total_cost:.2%} of the products) in {t:.2f}s, scaled by product count",
-    }
+        "build_items_per_s": n_items / med[bt],
+        "threads": bt,
+        "items_per_s_by_threads": {str(t): round(n_items / v, 1) for t, v in sorted(med.items())},
+        "sample": (f"every {stride}-th item of the cost-sorted list ({len(sample)} items, {c / total_cost:.2%} of the "
+                   f"products), median of 3 per thread count, scaled by product count"),
+    }  # fmt: skip
 
 
 # ---------------------------------------------------------------------------
-# main
+# data
 # ---------------------------------------------------------------------------
 
 
@@ -282,7 +328,6 @@ def run_reference(args, rank: int) -> None:
     """--impl reference: the CPU path (oracle port; Rust unavailable) on a bounded sample."""
     if rank != 0:
         return
-    import oracle
     from lkpy_b200 import data
 
     inter = make_data()
@@ -291,12 +336,10 @@ def run_reference(args, rank: int) -> None:
     p = (rng.standard_normal((inter.n_users, K)) * 0.1).astype(np.float32)
     q = (rng.standard_normal((inter.n_items, K)) * 0.1).astype(np.float32)
     threads = host_threads()
-    per_step = max(4.0, 120.0 / max(args.steps + args.warmup, 1))
-    vals = []
-    sample = ""
+    per_step = max(6.0, 150.0 / max(args.steps + args.warmup, 1))
+    vals, sample, r = [], "", {}
     for s in range(args.warmup + args.steps):
         r = cpu_als_epoch_estimate(ui, iu, p, q, per_step, threads)
-        threads = r["threads"]
         if s >= args.warmup:
             vals.append(r["epoch_ms"])
         sample = r["sample"]
@@ -307,7 +350,9 @@ def run_reference(args, rank: int) -> None:
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ML-25M-shaped synthetic ImplicitMFScorer features=64 (configs[1])",
                    "n_users": inter.n_users, "n_items": inter.n_items, "nnz": inter.nnz},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": r.get("threads"), "kind": "port", "sample": sample,
+                         "epoch_ms_by_threads": r.get("epoch_ms_by_threads"),
+                         "epoch_ms_8_threads": r.get("epoch_ms_8_threads")},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }  # fmt: skip
     emit(line)
@@ -324,6 +369,108 @@ def emit(line: dict) -> None:
     out.flush()
 
 
+# ---------------------------------------------------------------------------
+# parity at the benchmark's own shape (after the timed loops)
+# ---------------------------------------------------------------------------
+
+
+def als_parity(tr, inter, tag: str, rank: int, world: int, dev) -> dict | None:
+    """
+    One user half-step and one item half-step from fixed trained-scale factors on the trainer that was
+    just timed (single-GPU or sharded); rank 0 compares sampled rows with the f64 oracle
+    (oracle/parity.py).  At N > 1 additionally: the replicas of all ranks carry the same bits, and they
+    equal a single-GPU half-step run on rank 0.
+    """
+    import torch
+
+    from lkpy_b200 import engine
+
+    bf16 = tag == "bf16"
+    rng = np.random.default_rng(1234)
+    p0 = (rng.standard_normal((inter.n_users, K)) * 0.1).astype(np.float32)
+    q0 = (rng.standard_normal((inter.n_items, K)) * 0.1).astype(np.float32)
+    tp0, tq0 = torch.from_numpy(p0).to(dev), torch.from_numpy(q0).to(dev)
+    sharded = world > 1
+
+    def half(which: str):
+        tr.d_users.copy_(tp0)
+        tr.d_items.copy_(tq0)
+        tr.u_plan.status.zero_()
+        tr.i_plan.status.zero_()
+        if sharded:
+            import torch.distributed as dist
+
+            torch.cuda.synchronize()
+            dist.barrier()  # every replica holds (P0, Q0) before anyone's kernel writes into it
+            tr.half_step(which)
+            torch.cuda.synchronize()
+            dist.barrier()
+        elif which == "user":
+            tr._half(tr.u_plan, tr.d_users, tr.d_items, tr.d_items_bf16, tr.config.user_reg)
+        else:
+            tr._half(tr.i_plan, tr.d_items, tr.d_users, tr.d_users_bf16, tr.config.item_reg)
+        torch.cuda.synchronize()
+        tr._raise_on_status()
+        return (tr.d_users if which == "user" else tr.d_items).clone()
+
+    new_p = half("user")
+    new_q = half("item")
+    out: dict = {}
+    if sharded:
+        import torch.distributed as dist
+
+        from oracle import parity
+
+        cs = parity.checksum(new_p.cpu().numpy(), new_q.cpu().numpy())
+        # 64-bit checksums compared as two 32-bit halves (NCCL has no u64 min/max on every build)
+        t = torch.tensor([cs >> 32, cs & 0xFFFFFFFF], dtype=torch.int64, device=dev)
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["replicas_equal_across_ranks"] = bool(torch.equal(lo, hi))
+    if rank != 0:
+        return None
+    from oracle import parity
+
+    ui, iu = tr.ui_host, tr.iu_host
+    res = {}
+    for which, csr, old, other, new in (("user", ui, p0, q0, new_p), ("item", iu, q0, p0, new_q)):
+        rows = parity.sample_als_rows(csr.indptr, K, engine.DEFAULT_CHUNK_NNZ, seed=7)
+        got = new[torch.from_numpy(rows).to(dev)].cpu().numpy()
+        res[which] = parity.check_als_half("implicit", csr, rows, old[rows], other, got, REG, bf16)
+    out.update(res)
+    out["ok"] = bool(res["user"]["ok"] and res["item"]["ok"] and out.get("replicas_equal_across_ranks", True))
+    if sharded:
+        # the same two half-steps on one GPU (rank 0, full matrices): sharding must not change a bit
+        from lkpy_b200.als import ImplicitMFScorer, ImplicitMFTrainer
+        from lkpy_b200.components import Dataset, TrainingOptions
+
+        sc = ImplicitMFScorer(features=K, epochs=1, regularization=REG, weight=WEIGHT, gather_dtype=tr.config.gather_dtype)
+        single = ImplicitMFTrainer(sc, Dataset(inter), TrainingOptions(rng=42))
+        single.d_users.copy_(tp0)
+        single.d_items.copy_(tq0)
+        single._half(single.u_plan, single.d_users, single.d_items, single.d_items_bf16, REG)
+        eq_u = bool(torch.equal(single.d_users, new_p))
+        single.d_users.copy_(tp0)
+        single._half(single.i_plan, single.d_items, single.d_users, single.d_users_bf16, REG)
+        eq_i = bool(torch.equal(single.d_items, new_q))
+        out["equals_single_gpu_half_step"] = {"user": eq_u, "item": eq_i}
+        out["ok"] = bool(out["ok"] and eq_u and eq_i)
+        del single
+        torch.cuda.empty_cache()
+    log(f"[bench] parity ALS {tag}: user {res['user']['rel_fro_vs_f64_oracle']:.2e} "
+        f"item {res['item']['rel_fro_vs_f64_oracle']:.2e} (tol 1e-4) "
+        + (f"unrounded-oracle distance {res['user'].get('rel_fro_vs_unrounded_f64_oracle', 0):.2e} / "
+           f"{res['item'].get('rel_fro_vs_unrounded_f64_oracle', 0):.2e} " if bf16 else "")
+        + f"ok={out['ok']}")  # fmt: skip
+    return out
+
+
+# ---------------------------------------------------------------------------
+# main
+# ---------------------------------------------------------------------------
+
+
 def main() -> None:
     global _JSON_OUT
     sys.stdout.flush()
@@ -334,14 +481,20 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget per path")
+    ap.add_argument("--workload", default="ml25m", choices=["ml25m", "als100m", "knn1b"])
+    ap.add_argument("--cpu-seconds", type=float, default=18.0, help="CPU baseline budget per path")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--score-users", type=int, default=2048)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--score-batch", type=int, default=4096, help="users per scoring launch (all users are scored)")
+    ap.add_argument("--score-users", type=int, default=0, help="score only this many users (0 = all)")
     ap.add_argument("--variants", default="bf16,fp32", help="ALS gather dtypes to time (profiling runs pass one)")
-    ap.add_argument("--profile", action="store_true", help="under ncu: honour a small --warmup, skip e2e")
+    ap.add_argument("--profile", action="store_true", help="under ncu: honour a small --warmup, skip e2e/parity/CPU")
+    ap.add_argument("--scale", type=float, default=1.0, help="scale-out workloads: fraction of the full size (smoke runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.profile:
+        args.no_parity = args.no_cpu = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -353,7 +506,7 @@ def main() -> None:
 
     import torch
 
-    from lkpy_b200 import _build, _lib, data, engine
+    from lkpy_b200 import _build, _lib, data
     from lkpy_b200.als import ImplicitMFScorer, ImplicitMFTrainer
     from lkpy_b200.components import Dataset, TrainingOptions
 
@@ -369,6 +522,18 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=dev)
     peak, peak_src = load_peaks()
 
+    if args.workload != "ml25m":
+        import bench_scale
+
+        line = bench_scale.run(args, rank, world, dev, peak, peak_src)
+        if rank == 0:
+            emit(line)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+        return
+
     inter = make_data()
     ds = Dataset(inter)
 
@@ -380,18 +545,18 @@ def main() -> None:
         torch.cuda.synchronize()
 
     results: dict = {}
+    parity: dict = {}
     launches = 0
     variants = [v for v in args.variants.split(",") if v]
     for tag, gdt in (("bf16", "bfloat16"), ("fp32", "float32")):
         if tag not in variants:
             continue
+        scorer = ImplicitMFScorer(features=K, epochs=1, regularization=REG, weight=WEIGHT, gather_dtype=gdt)
         if world > 1:
             from lkpy_b200.parallel import ShardedImplicitMFTrainer
 
-            scorer = ImplicitMFScorer(features=K, epochs=1, regularization=REG, weight=WEIGHT, gather_dtype=gdt)
             tr = ShardedImplicitMFTrainer(scorer, ds, TrainingOptions(rng=42))
         else:
-            scorer = ImplicitMFScorer(features=K, epochs=1, regularization=REG, weight=WEIGHT, gather_dtype=gdt)
             tr = ImplicitMFTrainer(scorer, ds, TrainingOptions(rng=42))
         # one epoch from the reference init first, so timed epochs see trained-scale factors
         for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
@@ -404,7 +569,7 @@ def main() -> None:
         if tag == "bf16":
             for _ in range(3):  # every rank: the GPU stays under the same load while the sampler spins up
                 tr.train_epoch_device()
-        tr.kernel_events = []
+        graphed = bool(world > 1 and not args.profile and tr.enable_graph())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t_begin = time.time()
@@ -415,6 +580,12 @@ def main() -> None:
         barrier()
         t_end = time.time()
         clocks = sampler.stop(t_begin, t_end) if (rank == 0 and tag == "bf16") else None
+        # the same epochs once more with CUDA events around every row-solve launch (the roofline's
+        # kernel time; events cannot sit inside a captured graph, so this loop launches eagerly)
+        tr.kernel_events = []
+        for _ in range(args.steps):
+            tr.train_epoch_device()
+        barrier()
         ms = e0.elapsed_time(e1) / args.steps
         kern_ms = [a.elapsed_time(b) for a, b in tr.kernel_events]
         tr.kernel_events = None
@@ -439,21 +610,41 @@ def main() -> None:
             "solve_kernel_ms_per_epoch": per_epoch_kernel_ms,
             "roofline": {
                 "bound": "hbm",
-                "kernel": ("als_tc_kernel" if tag == "bf16" else "als_half_kernel") + " (user + item launch of one epoch)",
+                "kernel": tr.solve_kernel_name() + " (user + item launch of one epoch)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic("als_tc_kernel_epoch_bytes", world) if tag == "bf16" else None,
                 "algorithmic_bytes": alg, "peak_source": peak_src,
             },
             "clocks": clocks,
+            "cuda_graph": graphed,
         }  # fmt: skip
-        launches = 6 * args.steps
+        launches = tr.launches_per_epoch() * args.steps
         log(f"[bench] ALS {tag}: {ms:.3f} ms/epoch (solve kernels {per_epoch_kernel_ms:.3f} ms), "
             f"{achieved:.0f} GB/s algorithmic = {achieved / peak:.3f} of {peak_src}")
 
         # ---- end to end through the trainer API: factors from / to pinned host memory
-        if tag == "bf16" and not args.profile:
-            hp = torch.from_numpy(scorer.user_embeddings).pin_memory()
-            hq = torch.from_numpy(scorer.item_embeddings).pin_memory()
+        if not args.profile:
+            if world > 1:
+                # ONE host model shared by the ranks (/dev/shm, page-locked in every process)
+                from lkpy_b200.parallel import shared_pinned_tensor
+
+                names = (f"lkpy_b200_bench_p_{os.environ.get('MASTER_PORT', '0')}",
+                         f"lkpy_b200_bench_q_{os.environ.get('MASTER_PORT', '0')}")
+                shapes = (tuple(tr.d_users.shape), tuple(tr.d_items.shape))
+                if rank == 0:
+                    hp, hq = (shared_pinned_tensor(n, sh, create=True) for n, sh in zip(names, shapes))
+                    hp.copy_(tr.d_users)
+                    hq.copy_(tr.d_items)
+                barrier()
+                if rank != 0:
+                    hp, hq = (shared_pinned_tensor(n, sh) for n, sh in zip(names, shapes))
+                barrier()
+                if rank == 0:
+                    for n in names:
+                        os.unlink(f"/dev/shm/{n}")  # the mappings stay valid
+            else:
+                hp = torch.from_numpy(scorer.user_embeddings).pin_memory()
+                hq = torch.from_numpy(scorer.item_embeddings).pin_memory()
             for _ in range(2):
                 tr.train_epoch_e2e(hp, hq)
             barrier()
@@ -471,52 +662,61 @@ def main() -> None:
             if world > 1:
                 import torch.distributed as dist
 
-                # every rank uploads the rows it owns, rank 0 reads the whole model back: sum over ranks
+                # every rank moves the rows it owns (the PCIe links work in parallel): sum over ranks
                 t = torch.tensor([tr.e2e_bytes[0], tr.e2e_bytes[1], max(e2e_ms, wall)], device=dev, dtype=torch.float64)
                 tmax = t.clone()
                 dist.all_reduce(t)
                 dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
                 h2d, d2h = int(t[0].item()), int(t[1].item())
                 e2e_ms = wall = float(tmax[2].item())
-                api = ("ShardedImplicitMFTrainer.train_epoch_e2e: each rank uploads its row shards, NVLink all-gather, "
-                       "epoch, rank 0 reads the whole model back (others their shards); bytes summed over ranks")
-            results["e2e"] = {
+                api = ("ShardedImplicitMFTrainer.train_epoch_e2e: each rank uploads and downloads the row shards it "
+                       "owns into one shared pinned host model; bytes summed over ranks")
+            results[tag]["e2e"] = {
                 "value": max(e2e_ms, wall), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": api,
             }  # fmt: skip
-            log(f"[bench] ALS e2e: {results['e2e']['value']:.3f} ms/epoch")
-            if rank == 0 and world == 1 and not args.no_knn:
+            log(f"[bench] ALS {tag} e2e: {results[tag]['e2e']['value']:.3f} ms/epoch")
+            if tag == "bf16" and rank == 0 and world == 1 and not args.no_knn:
                 results["recommend"] = bench_recommend(args, tr, dev, peak, peak_src)
+        if not args.no_parity:
+            r = als_parity(tr, inter, tag, rank, world, dev)
+            if r is not None:
+                parity["als_" + tag] = r
         del tr, scorer
         torch.cuda.empty_cache()
 
     knn = None
     if not args.no_knn:
-        knn = bench_knn(args, inter, dev, peak, peak_src, rank, world)
+        knn = bench_knn(args, inter, dev, peak, peak_src, rank, world, parity)
 
     cpu = None
     if not args.no_cpu and rank == 0 and world == 1:
-        import oracle
-
         threads = host_threads()
         ui, iu = data.als_implicit_matrices(inter, WEIGHT)
         rng = np.random.default_rng(0)
         p = (rng.standard_normal((inter.n_users, K)) * 0.1).astype(np.float32)
         q = (rng.standard_normal((inter.n_items, K)) * 0.1).astype(np.float32)
         r = cpu_als_epoch_estimate(ui, iu, p, q, args.cpu_seconds, threads)
-        cpu = {"value": r["epoch_ms"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
-        log(f"[bench] CPU baseline ({r['threads']} threads): {r['epoch_ms']:.0f} ms/epoch  [{r['sample']}]")
-        if knn is not None:
-            kc = cpu_knn_estimate(knn.pop("_kui"), knn.pop("_kiu"), knn.pop("_cost"), args.cpu_seconds, threads)
-            knn["cpu_baseline"] = {"value": kc["build_items_per_s"], "unit": "items/s", "cores": threads,
-                                   "kind": "port", "sample": kc["sample"]}  # fmt: skip
-            log(f"[bench] CPU kNN build: {kc['build_items_per_s']:.0f} items/s [{kc['sample']}]")
+        cpu = {"value": r["epoch_ms"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"],
+               "epoch_ms_by_threads": r["epoch_ms_by_threads"], "epoch_ms_8_threads": r["epoch_ms_8_threads"],
+               "host_threads": threads}  # fmt: skip
+        log(f"[bench] CPU baseline ({r['threads']} threads): {r['epoch_ms']:.0f} ms/epoch "
+            f"(by threads {r['epoch_ms_by_threads']})  [{r['sample']}]")
+        if knn is not None and "_kui" in knn:
+            kc = cpu_knn_estimate(knn["_kui"], knn["_kiu"], knn["_cost"], args.cpu_seconds, threads)
+            knn["cpu_baseline"] = {"value": kc["build_items_per_s"], "unit": "items/s", "cores": kc["threads"],
+                                   "kind": "port", "sample": kc["sample"],
+                                   "items_per_s_by_threads": kc["items_per_s_by_threads"]}  # fmt: skip
+            log(f"[bench] CPU kNN build: {kc['build_items_per_s']:.0f} items/s at {kc['threads']} threads "
+                f"(by threads {kc['items_per_s_by_threads']}) [{kc['sample']}]")
     if knn is not None:
         for k_ in ("_kui", "_kiu", "_cost"):
             knn.pop(k_, None)
 
+    ok = all(v.get("ok", True) for v in parity.values()) if parity else None
     if rank == 0:
         head = results.get("bf16") or results["fp32"]
+        parity["ok"] = ok
         line = {
             "metric": METRIC, "value": head["ms_per_epoch"], "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_epoch"],
@@ -528,18 +728,24 @@ def main() -> None:
                 "weight": WEIGHT, "reg": REG, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                 "l2": "inputs (2 CSR orientations 400 MB + factors) exceed the 126 MB L2; no explicit flush",
             },
-            "roofline": head["roofline"], "clocks": head["clocks"], "e2e": results.get("e2e"),
+            "roofline": head["roofline"], "clocks": head["clocks"], "e2e": head.get("e2e"),
+            "cuda_graph": head.get("cuda_graph"),
             "gpu_launches": launches, "cpu_baseline": cpu,
-            "als_fp32": ({"ms_per_epoch": results["fp32"]["ms_per_epoch"], "roofline": results["fp32"]["roofline"]}
-                         if "fp32" in results else None),
+            "als_fp32": ({"ms_per_epoch": results["fp32"]["ms_per_epoch"], "roofline": results["fp32"]["roofline"],
+                          "e2e": results["fp32"].get("e2e")} if "fp32" in results else None),
             "knn": knn,
             "recommend": results.get("recommend"),
+            "parity": parity if not args.no_parity else None,
         }  # fmt: skip
         emit(line)
     if world > 1:
         import torch.distributed as dist
 
+        dist.barrier()
         dist.destroy_process_group()
+    if ok is False:
+        log("[bench] PARITY FAILURE — see the `parity` object")
+        raise SystemExit(1)
 
 
 def bench_recommend(args, tr, dev, peak, peak_src) -> dict:
@@ -609,18 +815,38 @@ def bench_recommend(args, tr, dev, peak, peak_src) -> dict:
     return out
 
 
-def bench_knn(args, inter, dev, peak, peak_src, rank: int = 0, world: int = 1) -> dict | None:
+def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: dict) -> dict | None:
     import torch
 
-    from lkpy_b200 import data, engine
+    from lkpy_b200 import accel, data, engine
+    from lkpy_b200.components import Dataset
 
     t0 = time.time()
     kui, kiu, means = data.knn_item_matrices(inter, True)
-    log(f"[bench] kNN host prep {time.time() - t0:.1f}s")
+    prep_s = time.time() - t0
+    log(f"[bench] kNN host prep {prep_s:.1f}s")
     d_ui = engine.DeviceCSR.from_host(kui, dev)
     d_iu = engine.DeviceCSR.from_host(kiu, dev)
 
     plan = engine.KnnBuildPlan.create(d_ui, d_iu)  # allocates the workspaces once
+    cost = plan.cost.cpu().numpy()
+    products = int(cost.sum()) - inter.nnz  # sim_row skips the diagonal entry of every (item, user) visit
+
+    def check_parity(indptr, cols, vals, extra: dict | None = None):
+        if args.no_parity or rank != 0:
+            return
+        from oracle import parity as par
+
+        rows = par.sample_knn_rows(cost, np.diff(kiu.indptr), seed=3)
+        r = par.check_knn_rows(kui, kiu, rows, indptr.cpu().numpy(), cols.cpu().numpy(), vals.cpu().numpy(),
+                               KNN_MIN_SIM, KNN_SAVE)  # fmt: skip
+        r["hottest_item_products"] = int(cost.max())
+        if extra:
+            r.update(extra)
+            r["ok"] = bool(r["ok"] and all(v for v in extra.values() if isinstance(v, bool)))
+        parity["knn_exact"] = r
+        log(f"[bench] parity kNN: {r['rows']} sampled rows ({r['neighbours_compared']} neighbours), "
+            f"mismatched {r['n_mismatched']} ok={r['ok']}")
 
     if world > 1:
         # item-sharded build: UI replicated, rows dealt by cost, one exchange of the top-K rows
@@ -629,7 +855,6 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int = 0, world: int = 1) -
         from lkpy_b200.parallel import sharded_knn_build_topk
 
         def sbuild():
-            plan.prepare()
             return sharded_knn_build_topk(plan, KNN_MIN_SIM, KNN_SAVE)
 
         sbuild()
@@ -646,8 +871,19 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int = 0, world: int = 1) -
         t = torch.tensor([s0.elapsed_time(s1) / reps], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        extra = None
+        if not args.no_parity:
+            from oracle import parity as par
+
+            cs = par.checksum(cols.cpu().numpy(), vals.cpu().numpy(), cnt.cpu().numpy())
+            tt = torch.tensor([cs >> 32, cs & 0xFFFFFFFF], dtype=torch.int64, device=dev)
+            lo, hi = tt.clone(), tt.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            extra = {"result_equal_across_ranks": bool(torch.equal(lo, hi))}
         if rank != 0:
             return None
+        check_parity(*engine.topk_rows_to_csr(cols, vals, cnt), extra=extra)
         log(f"[bench] kNN build x{world}: {ms:.1f} ms = {inter.n_items / (ms * 1e-3):.0f} items/s")
         return {
             "workload": "ML-25M-shaped synthetic ItemKNNScorer explicit, min_sim=1e-6, save_nbrs=20 (BASELINE configs[2])",
@@ -673,19 +909,6 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int = 0, world: int = 1) -
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    if os.environ.get("LK_BENCH_TRACE"):
-        # per-phase wall times with a sync after each phase (diagnostic only)
-        def tick(label, fn):
-            torch.cuda.synchronize()
-            t = time.perf_counter()
-            r = fn()
-            torch.cuda.synchronize()
-            log(f"[trace] {label}: {(time.perf_counter() - t) * 1e3:.2f} ms")
-            return r
-
-        p2 = tick("plan (geometry, tile pointers, cost, argsort)", lambda: engine.KnnBuildPlan.create(d_ui, d_iu))
-        r2 = tick("build_topk (accumulate + merge)", lambda: p2.build_topk(KNN_MIN_SIM, KNN_SAVE))
-        tick("rows -> CSR", lambda: engine.topk_rows_to_csr(*r2))
     # the accumulate kernel alone (same stream, events around the launch)
     import ctypes as C
 
@@ -702,8 +925,7 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int = 0, world: int = 1) -
     k1.record()
     torch.cuda.synchronize()
     kms = k0.elapsed_time(k1)
-    cost = plan.cost.cpu().numpy()
-    products = int(cost.sum()) - inter.nnz  # sim_row skips the diagonal entry of every (item, user) visit
+    del part_cols, part_vals, part_cnt
     nnz_out = int(csr[0][-1].item())
     alg = knn_build_bytes(products, inter.nnz, inter.n_users, inter.n_items, nnz_out)
     achieved = alg / (kms * 1e-3) / 1e9
@@ -724,35 +946,84 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int = 0, world: int = 1) -
     }  # fmt: skip
     log(f"[bench] kNN build: {ms:.1f} ms = {out['build_items_per_s']:.0f} items/s; accumulate kernel {kms:.1f} ms, "
         f"{achieved:.0f} GB/s algorithmic = {achieved / peak:.3f} of peak")
+    check_parity(*csr)
 
-    # scoring: a sample of users against every item
+    # ---- end to end through the plugin call: host CSR in -> host CSR out (item_train.rs:32-93)
+    if not args.profile:
+        accel.clear_cache()
+        accel.run_accel_task(accel.compute_similarities(kui, kiu, (inter.n_users, inter.n_items), KNN_MIN_SIM, KNN_SAVE))
+        ts = []
+        for _ in range(3):
+            accel.clear_cache()  # the device copies of the operands are part of the call
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = accel.run_accel_task(
+                accel.compute_similarities(kui, kiu, (inter.n_users, inter.n_items), KNN_MIN_SIM, KNN_SAVE)
+            )
+            ts.append(time.perf_counter() - t0)
+        e2e_s = float(np.median(ts))
+        h2d = int(sum(m.indptr.nbytes + m.indices.nbytes + m.values.nbytes for m in (kui, kiu)))
+        d2h = int(sum(r.indptr.nbytes + r.indices.nbytes + r.values.nbytes for r in res))
+        out["e2e"] = {
+            "value": inter.n_items / e2e_s, "unit": "items/s", "ms": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h,
+            "api": "accel.compute_similarities via run_accel_task: host CSR (UI, IU) in, host LargeList-layout CSR out",
+        }  # fmt: skip
+        accel.clear_cache()
+        # and through the component: ItemKNNScorer.train (host prep + upload + build + download)
+        from lkpy_b200.knn import ItemKNNScorer
+
+        m = ItemKNNScorer(max_nbrs=KNN_MAX_NBRS, min_sim=KNN_MIN_SIM, save_nbrs=KNN_SAVE)
+        t0 = time.perf_counter()
+        m.train(Dataset(inter))
+        torch.cuda.synchronize()
+        out["train_e2e_ms"] = (time.perf_counter() - t0) * 1e3
+        out["train_prep"] = m.__dict__.get("prep_where", "host (SciPy)")
+        del m
+        log(f"[bench] kNN e2e: compute_similarities {e2e_s * 1e3:.0f} ms = {out['e2e']['value']:.0f} items/s; "
+            f"ItemKNNScorer.train {out['train_e2e_ms']:.0f} ms ({out['train_prep']} prep)")
+
+    # ---- scoring: every user's history against every item, in batches
     indptr, c, v = csr
     st = engine.KnnScorerState.create(inter.n_items, indptr, c, v, dev)
-    rng = np.random.default_rng(5)
-    nq = min(args.score_users, inter.n_users)
-    users = np.sort(rng.choice(inter.n_users, nq, replace=False))
     R = inter.coo().tocsr()
-    lens = np.diff(R.indptr)[users]
-    ref_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    idx = np.concatenate([np.arange(R.indptr[u], R.indptr[u + 1]) for u in users])
-    ri = R.indices[idx].astype(np.int32)
-    rv = (R.data[idx] - means[ri]).astype(np.float32)
-    tgt_ptr = (np.arange(nq + 1, dtype=np.int64) * inter.n_items)
-    ti = np.tile(np.arange(inter.n_items, dtype=np.int32), nq)
-    d = lambda x: torch.from_numpy(x).to(dev)  # noqa: E731
-    d_args = (d(ref_ptr), d(ri), d(rv), d(tgt_ptr), d(ti))
-    st.score(*d_args, 20, 1)
-    torch.cuda.synchronize()
-    e0.record()
-    sc, ct = st.score(*d_args, 20, 1)
-    e1.record()
-    torch.cuda.synchronize()
-    sms = e0.elapsed_time(e1)
+    n_score = inter.n_users if args.score_users <= 0 else min(args.score_users, inter.n_users)
+    B = max(1, min(args.score_batch, n_score))
+    all_items = torch.arange(inter.n_items, dtype=torch.int32, device=dev)
+    row_len = (indptr[1:] - indptr[:-1]).cpu().numpy()
+    d_ri = torch.from_numpy(R.indices.astype(np.int32)).to(dev)
+    d_rv = torch.from_numpy((R.data - means[R.indices]).astype(np.float32)).to(dev)
+    tgt_items = all_items.repeat(B)
+    total_ms, scored, touched = 0.0, 0, 0
+    finite = 0
+    for u0 in range(0, n_score, B):
+        u1 = min(u0 + B, n_score)
+        nb = u1 - u0
+        a0, a1 = int(R.indptr[u0]), int(R.indptr[u1])
+        ref_ptr = torch.from_numpy((R.indptr[u0 : u1 + 1] - a0).astype(np.int64)).to(dev)
+        tgt_ptr = torch.arange(nb + 1, dtype=torch.int64, device=dev) * inter.n_items
+        if u0 == 0:  # warm-up launch
+            st.score(ref_ptr, d_ri[a0:a1], d_rv[a0:a1], tgt_ptr, tgt_items[: nb * inter.n_items], KNN_MAX_NBRS, 1)
+        e0.record()
+        sc, ct = st.score(ref_ptr, d_ri[a0:a1], d_rv[a0:a1], tgt_ptr, tgt_items[: nb * inter.n_items], KNN_MAX_NBRS, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        scored += nb
+        touched += int(row_len[R.indices[a0:a1]].sum())
+        finite += int(torch.isfinite(sc).sum().item())
+        del sc, ct
+    alg_s = knn_score_bytes(touched, int(R.indptr[n_score]), scored * inter.n_items)
+    ach_s = alg_s / (total_ms * 1e-3) / 1e9
     out["score"] = {
-        "users": nq, "targets_per_user": inter.n_items, "ms": sms, "users_per_s": nq / (sms * 1e-3),
-        "scored_fraction": float(torch.isfinite(sc).float().mean().item()),
+        "users": scored, "targets_per_user": inter.n_items, "batch": B, "ms": total_ms,
+        "users_per_s": scored / (total_ms * 1e-3), "scored_fraction": finite / max(scored * inter.n_items, 1),
+        "roofline": {"bound": "hbm", "kernel": st.kernel_name(), "achieved": ach_s, "peak": peak, "unit": "GB/s",
+                     "frac": ach_s / peak, "traffic": None, "algorithmic_bytes": alg_s, "peak_source": peak_src},
     }  # fmt: skip
-    log(f"[bench] kNN score: {nq} users x all items in {sms:.1f} ms = {out['score']['users_per_s']:.0f} users/s")
+    out["build_plus_score_s"] = ms * 1e-3 + total_ms * 1e-3 * (inter.n_users / max(scored, 1))
+    log(f"[bench] kNN score: {scored} users x all items in {total_ms:.1f} ms = {out['score']['users_per_s']:.0f} users/s, "
+        f"{ach_s:.0f} GB/s algorithmic = {ach_s / peak:.3f} of peak")
     return out
 
 

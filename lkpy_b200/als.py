@@ -259,7 +259,8 @@ class ALSTrainerBase(ModelTrainer):
         raise NotImplementedError
 
     # -- epoch ---------------------------------------------------------------
-    def _half(self, plan, this, other, other_bf16, reg: float, replicas=None, replica_row0: int = 0) -> torch.Tensor:
+    def _half(self, plan, this, other, other_bf16, reg: float, replicas=None, replica_row0: int = 0,
+              before_solve=None) -> torch.Tensor:  # fmt: skip
         plan.sqdelta.zero_()
         otor = None
         gather = other
@@ -270,6 +271,8 @@ class ALSTrainerBase(ModelTrainer):
         elif other_bf16 is not None:
             other_bf16.copy_(other)
             gather = other_bf16
+        if before_solve is not None:
+            before_solve()  # e.g. wait for the upload of `this` that ran beside the OtOr pass
         if self.kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -290,6 +293,18 @@ class ALSTrainerBase(ModelTrainer):
         self.epochs_trained += 1
         return du, di
 
+    def solve_kernel_name(self) -> str:
+        """Which row-solve kernel the configuration runs (bench.py's roofline label)."""
+        k = self.config.embedding_size
+        tc = k == 64 and _lib.get_option("LK_ALS_TC") != 0
+        if tc and (self.bf16 or _lib.get_option("LK_ALS_TF32") != 0):
+            return "als_tc_kernel"
+        return "als_half_kernel"
+
+    def launches_per_epoch(self) -> int:
+        """Kernels of this library launched by one epoch (two halves: OtOr partial + reduce + row solve)."""
+        return 6 if self.MODE == _lib.LK_ALS_IMPLICIT else 2
+
     def _raise_on_status(self) -> None:
         for plan in (self.u_plan, self.i_plan):
             st = int(plan.status.item())
@@ -302,16 +317,37 @@ class ALSTrainerBase(ModelTrainer):
         self._raise_on_status()
         return {"deltaP": float(np.sqrt(du.item())), "deltaQ": float(np.sqrt(di.item()))}
 
+    def _copy_stream(self) -> torch.cuda.Stream:
+        s = self.__dict__.get("_copy_stream_obj")
+        if s is None:
+            s = self.__dict__["_copy_stream_obj"] = torch.cuda.Stream(device=self.device)
+        return s
+
     def train_epoch_e2e(self, host_users: torch.Tensor, host_items: torch.Tensor) -> dict[str, float]:
         """
         One epoch with the factor tables taken from, and returned to, pinned host
         tensors (the host-array contract of ``train_*_matrix``); the CSR stays in HBM.
+        The copies that do not sit on the dependency chain are hidden: Q goes up first (the user
+        half's OtOr pass starts on it while P is still in flight on the copy stream), and P — final
+        after the user half — comes down on the copy stream underneath the item half.
         """
-        self.d_users.copy_(host_users, non_blocking=True)
+        main = torch.cuda.current_stream()
+        side = self._copy_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.d_users.copy_(host_users, non_blocking=True)  # old P: only the Δ-norm needs it
         self.d_items.copy_(host_items, non_blocking=True)
-        du, di = self.train_epoch_device()
-        host_users.copy_(self.d_users, non_blocking=True)
+        self.u_plan.status.zero_()
+        self.i_plan.status.zero_()
+        du = self._half(self.u_plan, self.d_users, self.d_items, self.d_items_bf16, self.config.user_reg,
+                        before_solve=lambda: main.wait_stream(side))  # fmt: skip
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            host_users.copy_(self.d_users, non_blocking=True)  # under the item half
+        di = self._half(self.i_plan, self.d_items, self.d_users, self.d_users_bf16, self.config.item_reg)
+        self.epochs_trained += 1
         host_items.copy_(self.d_items, non_blocking=True)
+        main.wait_stream(side)
         deltas = torch.cat([du, di]).cpu()  # device->host read of the step's result; synchronises
         return {"deltaP": float(np.sqrt(deltas[0])), "deltaQ": float(np.sqrt(deltas[1]))}
 

@@ -392,6 +392,10 @@ class KnnScorerState:
     HEAP_TARGETS_PER_WARP = 2048
     USE_LISTS = True  # list-based kernel (parallel over the history); False: the sequential kernel
 
+    def kernel_name(self) -> str:
+        lists = self.USE_LISTS and _lib.get_option("LK_KNN_SCORE_SEQ") != 1
+        return "knn_score_lists_kernel" if lists else "knn_score_kernel"
+
     def _slotmap(self, n_queries: int) -> tuple[torch.Tensor, int]:
         """One slot-map row per working warp: min(n_queries, full grid) rows (a single query takes
         n_items * 4 B, not grid * n_items * 4 B)."""

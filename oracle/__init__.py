@@ -28,12 +28,59 @@ _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 
+_FAST_PATH = _DIR / "liblk_cpu_fast.so"
+_fast = None
+
+
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc, no GPU needed)."""
-    src = _DIR / "lk_oracle.c"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
-        subprocess.run(["make", "-C", str(_DIR), "-s"], check=True)
+    stale = force
+    for so, src in ((_LIB_PATH, _DIR / "lk_oracle.c"), (_FAST_PATH, _DIR / "lk_cpu_fast.c")):
+        stale = stale or not so.exists() or so.stat().st_mtime < src.stat().st_mtime
+    if stale:
+        subprocess.run(["make", "-C", str(_DIR), "-s"] + (["-B"] if force else []), check=True)
     return _LIB_PATH
+
+
+def fast_lib():
+    """``liblk_cpu_fast.so``: the many-core restatement of the ALS half-epoch timed as the CPU baseline."""
+    global _fast
+    if _fast is None:
+        build()
+        L = C.CDLL(str(_FAST_PATH))
+        L.lk_cpu_als_half_f32.argtypes = [
+            C.c_int, _i64p, _i32p, _f32p, C.c_int64, C.c_int, _f32p, _f32p, C.c_void_p,
+            C.c_float, C.c_int, C.POINTER(C.c_double),
+        ]  # fmt: skip
+        L.lk_cpu_als_half_f32.restype = C.c_int64
+        _fast = L
+    return _fast
+
+
+def als_half_fast(
+    mode: str, matrix, this: np.ndarray, other: np.ndarray, *, otor_mat: np.ndarray | None = None,
+    reg: float = 0.0, threads: int = 0, inplace: bool = False,
+) -> tuple[np.ndarray, float]:
+    """
+    The timed CPU baseline: same half-epoch as ``als_half`` through ``lk_cpu_fast.c`` (thread-private
+    register-blocked Gram, vectorised Cholesky; scales on many-core hosts).  ``inplace`` skips the
+    defensive copy of ``this`` (timing runs).
+    """
+    indptr, cols, vals = _csr_parts(matrix)
+    this = np.ascontiguousarray(this, dtype=np.float32) if inplace else np.array(this, dtype=np.float32, order="C")
+    other = np.ascontiguousarray(other, dtype=np.float32)
+    n_rows, k = this.shape
+    m = 0 if mode == "implicit" else 1
+    op = None
+    if m == 0:
+        assert otor_mat is not None
+        otor_mat = np.ascontiguousarray(otor_mat, dtype=np.float32)
+        op = otor_mat.ctypes.data_as(C.c_void_p)
+    sq = C.c_double(0.0)
+    fail = fast_lib().lk_cpu_als_half_f32(m, indptr, cols, vals, n_rows, k, this, other, op, reg, threads, C.byref(sq))
+    if fail:
+        raise RuntimeError(f"ALS solve error: row {fail - 1} not positive definite")
+    return this, float(np.sqrt(sq.value))
 
 
 def lib():
@@ -65,6 +112,10 @@ def lib():
             C.c_int64, C.c_int64, C.c_int64, C.c_int,
         ]  # fmt: skip
         L.lk_oracle_knn_build.restype = C.c_void_p
+        L.lk_oracle_knn_build_rows.argtypes = [
+            _i64p, _i32p, _f32p, _i64p, _i32p, _f32p, C.c_int64, C.c_float, C.c_int64, _i64p, C.c_int64, C.c_int,
+        ]  # fmt: skip
+        L.lk_oracle_knn_build_rows.restype = C.c_void_p
         for nm, rt in (
             ("lk_oracle_csr_indptr", C.POINTER(C.c_int64)),
             ("lk_oracle_csr_cols", C.POINTER(C.c_int32)),
@@ -274,20 +325,43 @@ def als_half_f64(
     return out, float(np.sqrt(sq.value))
 
 
+_parts_cache: dict = {}
+
+
+def knn_operands(ui, iu):
+    """The six contiguous arrays ``knn_build`` passes to C, converted once (int64 offsets) and kept
+    for repeated calls on the same pair of matrices (row-by-row parity checks, timing repeats)."""
+    key = (id(ui), id(iu))
+    ent = _parts_cache.get(key)
+    if ent is None or ent[0] is not ui or ent[1] is not iu:
+        _parts_cache.clear()
+        ent = (ui, iu, _csr_parts(ui), _csr_parts(iu))
+        _parts_cache[key] = ent
+    return ent[2], ent[3]
+
+
 def knn_build(
-    ui, iu, min_sim: float, save_nbrs: int | None, rows: tuple[int, int] | None = None, threads: int = 0
+    ui, iu, min_sim: float, save_nbrs: int | None, rows: tuple[int, int] | None = None, threads: int = 0,
+    row_list: np.ndarray | None = None,
 ) -> sps.csr_array:
-    """``compute_similarities`` (item_train.rs:32-152) → CSR with int64 offsets."""
-    uip, uic, uiv = _csr_parts(ui)
-    iup, iuc, iuv = _csr_parts(iu)
+    """``compute_similarities`` (item_train.rs:32-152) → CSR with int64 offsets.  ``rows`` = a
+    contiguous range of item rows, ``row_list`` = an explicit list (result rows in list order)."""
+    (uip, uic, uiv), (iup, iuc, iuv) = knn_operands(ui, iu)
     n_users = len(uip) - 1
     n_items = len(iup) - 1
-    rb, re = rows if rows is not None else (0, n_items)
     L = lib()
-    h = L.lk_oracle_knn_build(
-        uip, uic, uiv, iup, iuc, iuv, n_users, n_items, np.float32(min_sim),
-        int(save_nbrs) if save_nbrs else 0, rb, re, threads,
-    )  # fmt: skip
+    if row_list is not None:
+        rl = np.ascontiguousarray(row_list, dtype=np.int64)
+        h = L.lk_oracle_knn_build_rows(
+            uip, uic, uiv, iup, iuc, iuv, n_items, np.float32(min_sim),
+            int(save_nbrs) if save_nbrs else 0, rl, len(rl), threads,
+        )  # fmt: skip
+    else:
+        rb, re = rows if rows is not None else (0, n_items)
+        h = L.lk_oracle_knn_build(
+            uip, uic, uiv, iup, iuc, iuv, n_users, n_items, np.float32(min_sim),
+            int(save_nbrs) if save_nbrs else 0, rb, re, threads,
+        )  # fmt: skip
     try:
         nr = L.lk_oracle_csr_rows(h)
         indptr = np.ctypeslib.as_array(L.lk_oracle_csr_indptr(h), shape=(nr + 1,)).copy()

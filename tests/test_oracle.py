@@ -212,3 +212,53 @@ def test_synth_shape_small():
     ni = np.bincount(inter.items, minlength=800)
     assert nu.max() > 10 * np.median(nu[nu > 0])  # heavy-tailed users
     assert ni.max() > 5 * np.median(ni[ni > 0])
+
+
+def test_cpu_fast_baseline_matches_oracle():
+    """oracle/lk_cpu_fast.c (the timed many-core CPU baseline) is the same half-epoch as lk_oracle.c."""
+    inter = small_synth(700, 450, 30000, seed=4)
+    ui, iu = data.als_implicit_matrices(inter, 40.0, use_ratings=True)
+    rng = np.random.default_rng(4)
+    for k in (64, 32, 128, 20):
+        p = (rng.standard_normal((inter.n_users, k)) * 0.1).astype(np.float32)
+        q = (rng.standard_normal((inter.n_items, k)) * 0.1).astype(np.float32)
+        o32, o64 = oracle.otor(q, 0.1)
+        ref, dref = oracle.als_half_f64("implicit", ui, p, q, otor_mat=o64)
+        fast, dfast = oracle.als_half_fast("implicit", ui, p, q, otor_mat=o32, threads=3)
+        assert rel_fro(fast, ref) < 1e-4
+        assert dfast == pytest.approx(dref, rel=1e-4)
+        ref, _ = oracle.als_half_f64("explicit", iu, q, p, reg=0.05)
+        fast, _ = oracle.als_half_fast("explicit", iu, q, p, reg=0.05, threads=2)
+        assert rel_fro(fast, ref) < 1e-4
+        assert np.all(fast[np.diff(iu.indptr) == 0] == 0.0)
+
+
+def test_parity_helpers_on_oracle_output():
+    """oracle/parity.py: the sampled-row checks accept the oracle's own output and flag a corrupted one."""
+    from oracle import parity
+
+    inter = small_synth(900, 500, 40000, seed=12)
+    ui, iu = data.als_implicit_matrices(inter, 40.0)
+    rng = np.random.default_rng(12)
+    p = (rng.standard_normal((inter.n_users, 64)) * 0.1).astype(np.float32)
+    q = (rng.standard_normal((inter.n_items, 64)) * 0.1).astype(np.float32)
+    o32, _ = oracle.otor(q, 0.1)
+    new, _ = oracle.als_half("implicit", ui, p, q, otor_mat=o32)
+    rows = parity.sample_als_rows(ui.indptr, 64, 128, n_random=200, seed=1)
+    assert np.any(np.diff(ui.indptr)[rows] > 128)
+    r = parity.check_als_half("implicit", ui, rows, p[rows], q, new[rows], 0.1, bf16=False)
+    assert r["ok"] and r["rel_fro_vs_f64_oracle"] < 1e-4
+    bad = new[rows].copy()
+    bad[3] *= 1.01
+    assert not parity.check_als_half("implicit", ui, rows, p[rows], q, bad, 0.1, bf16=False)["ok"]
+
+    kui, kiu, _ = data.knn_item_matrices(inter, True)
+    S = oracle.knn_build(kui, kiu, 1e-6, 20)
+    cost = np.asarray((kiu.to_scipy() @ np.diff(kui.indptr).astype(np.float64))).ravel()
+    krows = parity.sample_knn_rows(cost, np.diff(kiu.indptr), n_random=50, seed=2)
+    assert parity.check_knn_rows(kui, kiu, krows, S.indptr, S.indices, S.data, 1e-6, 20)["ok"]
+    vals = S.data.copy()
+    vals[S.indptr[krows[0]]] = np.nextafter(vals[S.indptr[krows[0]]], np.float32(2.0))
+    res = parity.check_knn_rows(kui, kiu, krows, S.indptr, S.indices, vals, 1e-6, 20)
+    assert not res["ok"] and res["mismatched_rows"] == [int(krows[0])]
+    assert parity.checksum(vals) != parity.checksum(S.data)
