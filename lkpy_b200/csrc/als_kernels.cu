@@ -447,7 +447,8 @@ __global__ void otor_reduce_kernel(const float *__restrict__ partial, int nblock
     }
 }
 
-int launch_als_tc(const lk_als_args &a, cudaStream_t st);  // als_tc.cu (tensor-core Gram + in-TMEM solve)
+int launch_als_tc(const lk_als_args &a, cudaStream_t st);   // als_tc.cu  (bf16 rows, uniform weights)
+int launch_als_tcx(const lk_als_args &a, cudaStream_t st);  // als_tcx.cu (fp32 rows / non-uniform weights, tf32 x3)
 
 static int pad_features(int k) { return k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : -1; }
 
@@ -589,7 +590,9 @@ int lk_als_half_epoch(const lk_als_args *args, void *stream)
     // k = 64: tensor-core kernel (als_tc.cu) unless switched off (option LK_ALS_TC = 0) or the
     // configuration is outside what it covers (returns 1: fall through to the SIMT kernel)
     if (options().als_tc != 0) {
-        const int rc = launch_als_tc(a, st);
+        int rc = launch_als_tc(a, st);
+        if (rc <= 0) return rc;
+        rc = launch_als_tcx(a, st);
         if (rc <= 0) return rc;
     }
     if (a.other_dtype == LK_DTYPE_F32) return dispatch_k<float>(a, st);

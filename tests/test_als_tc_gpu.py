@@ -140,8 +140,9 @@ def test_tc_zero_weight_falls_back(cuda_lib, lk_options):
     assert rel_fro(got, ref) < 1e-4
 
 
-def test_tc_non_uniform_weights_fall_back(cuda_lib, lk_options):
-    """use_ratings=True confidences are not uniform: the SIMT kernel must take the launch."""
+def test_tc_non_uniform_weights_leave_the_bf16_fast_path(cuda_lib, lk_options):
+    """use_ratings=True confidences are not uniform: als_tc.cu declines, als_tcx.cu (or, switched off, the
+    SIMT kernel) takes the launch."""
     _set(lk_options, "tc-cholesky")
     inter = small_synth(400, 300, 15000, seed=8)
     ui, _ = data.als_implicit_matrices(inter, 40.0, use_ratings=True)
