@@ -828,7 +828,7 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
     d_ui = engine.DeviceCSR.from_host(kui, dev)
     d_iu = engine.DeviceCSR.from_host(kiu, dev)
 
-    plan = engine.KnnBuildPlan.create(d_ui, d_iu)  # allocates the workspaces once
+    plan = engine.KnnBuildPlan.create(d_ui, d_iu, world=world)  # allocates the workspaces once
     cost = plan.cost.cpu().numpy()
     products = int(cost.sum()) - inter.nnz  # sim_row skips the diagonal entry of every (item, user) visit
 
@@ -855,6 +855,7 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
         from lkpy_b200.parallel import sharded_knn_build_topk
 
         def sbuild():
+            plan.prepare()  # tile pointers, costs, units: part of the build, as at N = 1
             return sharded_knn_build_topk(plan, KNN_MIN_SIM, KNN_SAVE)
 
         sbuild()
@@ -914,11 +915,11 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
 
     from lkpy_b200 import _lib
 
-    n_items, H = plan.geom.n_items, plan.geom.n_halves
-    part_cols = torch.empty(n_items * H * KNN_SAVE, dtype=torch.int32, device=dev)
-    part_vals = torch.empty(n_items * H * KNN_SAVE, dtype=torch.float32, device=dev)
-    part_cnt = torch.zeros(n_items * H, dtype=torch.int32, device=dev)
-    a = plan._args(plan.order, KNN_MIN_SIM, KNN_SAVE)
+    u = plan.units(split_hot=True)
+    part_cols = torch.empty(u["n_units"] * KNN_SAVE, dtype=torch.int32, device=dev)
+    part_vals = torch.empty(u["n_units"] * KNN_SAVE, dtype=torch.float32, device=dev)
+    part_cnt = torch.zeros(u["n_units"], dtype=torch.int32, device=dev)
+    a = plan._args(u, u["sched"], KNN_MIN_SIM, KNN_SAVE)
     a.d_part_cols, a.d_part_vals, a.d_part_cnt = _lib.ptr(part_cols), _lib.ptr(part_vals), _lib.ptr(part_cnt)
     k0.record()
     _lib.check(_lib.lib().lk_knn_build(C.byref(a), _lib.stream_ptr()), "lk_knn_build")
@@ -937,7 +938,7 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
         "products": products,
         "neighbours_kept": nnz_out,
         "geometry": {"warps": plan.geom.warps, "tile_cols": plan.geom.tile_cols, "halves": plan.geom.n_halves,
-                     "ctas_per_sm": plan.geom.ctas_per_sm},
+                     "ctas_per_sm": plan.geom.ctas_per_sm, "work_units": u["n_units"]},
         "roofline": {"bound": "hbm", "kernel": "knn_build_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic("knn_build_kernel_bytes", world), "algorithmic_bytes": alg,
@@ -963,7 +964,7 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
             ts.append(time.perf_counter() - t0)
         e2e_s = float(np.median(ts))
         h2d = int(sum(m.indptr.nbytes + m.indices.nbytes + m.values.nbytes for m in (kui, kiu)))
-        d2h = int(sum(r.indptr.nbytes + r.indices.nbytes + r.values.nbytes for r in res))
+        d2h = int(sum(r.nbytes for r in res))  # LargeList chunks: offsets + index + value buffers
         out["e2e"] = {
             "value": inter.n_items / e2e_s, "unit": "items/s", "ms": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h,

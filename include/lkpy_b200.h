@@ -128,6 +128,11 @@ typedef struct lk_als_args {
                                 ratings): lets the Gram run on the tensor cores as v * M^T M */
     float uniform_val;
     unsigned long long *d_prof; /* optional [8] per-phase SM-cycle counters (diagnostics), or NULL */
+    /* Cooperative cancel (the role of CancelAdapter, src/accel/als/implicit.rs:72-73, tasks/mod.rs:62-106):
+     * optional device flag, read (uncached) every time a CTA fetches work; once non-zero no further rows
+     * are started — rows already solved keep their new values, the rest their old ones.  Progress =
+     * *d_work_counter (groups of rows handed out so far), readable from another stream while the kernel runs. */
+    const int32_t *d_cancel;
 } lk_als_args;
 
 LK_API int lk_als_half_epoch(const lk_als_args *args, void *stream);
@@ -174,21 +179,31 @@ typedef struct lk_knn_build_args {
     const int32_t *d_ui_indptr, *d_ui_cols; const float *d_ui_vals; /* users x items */
     const int32_t *d_iu_indptr, *d_iu_cols; const float *d_iu_vals; /* items x users */
     const int32_t *d_tile_ptr;
-    const int32_t *d_order;  /* [n_work] item ids to process, most expensive first */
+    /* Work units.  d_units [n_units * 4] = {item, half, piece, n_pieces} stored item-major (an
+     * item's units are d_unit_ptr[item] .. d_unit_ptr[item+1], halves and pieces ascending);
+     * n_pieces in {1, 2, 4, 8} cuts the (item, half) unit of a very expensive item into column
+     * slices so that several CTAs share it (only with save_nbrs > 0; the unbounded build needs
+     * n_pieces == 1).  d_sched [n_work]: the unit ids to process, most expensive first — the
+     * rows of a subset of items (item-sharded build) are produced by listing only their units. */
+    const int32_t *d_units;
+    const int32_t *d_unit_ptr; /* [n_items + 1] */
+    int32_t max_units_per_item;
+    const int32_t *d_sched;
     int64_t n_work;
     float min_sim;           /* keep dots >= min_sim (item_train.rs:133-137) */
     int32_t save_nbrs;       /* > 0: keep top-K per row (item_train.rs:140-147); <= 0: unbounded */
-    /* truncated mode: per (item, half) partial lists, then merged */
-    int32_t *d_part_cols;    /* [n_items * n_halves * K] */
-    float *d_part_vals;      /* [n_items * n_halves * K] */
-    int32_t *d_part_cnt;     /* [n_items * n_halves] */
+    /* truncated mode: per-unit partial lists, then merged */
+    int32_t *d_part_cols;    /* [n_units * K] */
+    float *d_part_vals;      /* [n_units * K] */
+    int32_t *d_part_cnt;     /* [n_units] */
     /* unbounded mode: bump-allocated candidate pool */
     int32_t *d_pool_cols; float *d_pool_vals; int64_t pool_capacity;
-    int64_t *d_pool_off;     /* [n_items * n_halves] offsets into the pool */
+    int64_t *d_pool_off;     /* [n_units] offsets into the pool */
     unsigned long long *d_pool_cursor; /* [1] zeroed by the caller */
     int32_t *d_tie_scratch;  /* [grid * half_cols * 3] per-CTA scratch for tie resolution */
-    int32_t *d_work_counter; /* [1] zeroed by the call */
+    int32_t *d_work_counter; /* [1] zeroed by the call; = work units handed out so far (progress) */
     int32_t *d_status;       /* [1] 0 ok; 1 pool overflow; 2 NaN similarity */
+    const int32_t *d_cancel; /* optional device flag (see lk_als_args.d_cancel): non-zero stops the hand-out of work */
 } lk_knn_build_args;
 
 LK_API int64_t lk_knn_tie_scratch_ints(const lk_knn_geom *geom);
@@ -205,6 +220,23 @@ LK_API int lk_knn_merge_topk(const lk_knn_build_args *args, int32_t *d_out_cols,
  * d_out_indptr [n_items+1] (int64, exclusive scan of the per-row counts). */
 LK_API int lk_knn_pool_to_csr(const lk_knn_build_args *args, const int64_t *d_out_indptr,
                        int32_t *d_out_cols, float *d_out_vals, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* item-kNN input preparation                               */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Mean-centre (centre != 0: explicit feedback) and unit-L2-normalise the item columns of the rating
+ * matrix — the host stage of ItemKNNScorer.train, src/lenskit/knn/item.py:202-228
+ * (_center_ratings, _normalize_rows), reproduced bit for bit (NumPy's pairwise float32 / float64
+ * summation order, float64 norm and reciprocal, float32 result; see prep.cu).
+ * d_indptr [n_cols+1] / d_vals [nnz]: the ratings in CSC order (items major, users ascending);
+ * d_means [n_cols] (may be NULL) receives the float32 item means (0 for empty items and when not
+ * centring); d_out [nnz] the normalised values in the same order — together with the user
+ * indices this is the IU matrix compute_similarities takes, and its transpose is UI.
+ */
+LK_API int lk_knn_prep_columns(const int32_t *d_indptr, const float *d_vals, int32_t n_cols, int32_t centre,
+                               float *d_means, float *d_out, void *stream);
 
 /* ------------------------------------------------------------------------- */
 /* item-kNN scoring (batched over queries)                                    */
@@ -246,6 +278,14 @@ typedef struct lk_knn_score_args {
     void *d_pool;
     int64_t pool_entries;
     unsigned long long *d_pool_cursor;
+    /* 0: item-kNN (above).  1: user-kNN scoring, src/accel/knn/user_score.rs:21-98 — the same
+     * accumulators with the roles of the two operands swapped: the "history" of a query is its
+     * neighbour list (d_ref_items = neighbour user rows, d_ref_vals = their similarities = the
+     * WEIGHTS, required), the matrix is the users x items rating matrix (d_sim_* = its CSR;
+     * d_sim_vals = centred ratings = the VALUES, NULL for implicit feedback), n_items = its number
+     * of columns, and a row index is valid in [0, n_matrix_rows). */
+    int32_t user_mode;
+    int32_t n_matrix_rows;       /* user mode: rows of the rating matrix (item mode: unused, = n_items) */
 } lk_knn_score_args;
 
 /* largest number of warps the scoring grid runs (one slotmap row each) */

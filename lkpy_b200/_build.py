@@ -16,7 +16,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "liblkpy_b200.so"
-SOURCES = ["capi.cu", "als_kernels.cu", "als_tc.cu", "als_tcx.cu", "knn_build.cu", "knn_score.cu", "topn.cu"]
+SOURCES = ["capi.cu", "als_kernels.cu", "als_tc.cu", "als_tcx.cu", "knn_build.cu", "knn_score.cu", "topn.cu", "prep.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",

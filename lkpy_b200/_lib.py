@@ -58,6 +58,7 @@ class LkAlsArgs(C.Structure):
         ("vals_uniform", C.c_int32),
         ("uniform_val", C.c_float),
         ("d_prof", vp),
+        ("d_cancel", vp),
     ]
 
 
@@ -84,7 +85,10 @@ class LkKnnBuildArgs(C.Structure):
         ("d_iu_cols", vp),
         ("d_iu_vals", vp),
         ("d_tile_ptr", vp),
-        ("d_order", vp),
+        ("d_units", vp),
+        ("d_unit_ptr", vp),
+        ("max_units_per_item", C.c_int32),
+        ("d_sched", vp),
         ("n_work", C.c_int64),
         ("min_sim", C.c_float),
         ("save_nbrs", C.c_int32),
@@ -99,6 +103,7 @@ class LkKnnBuildArgs(C.Structure):
         ("d_tie_scratch", vp),
         ("d_work_counter", vp),
         ("d_status", vp),
+        ("d_cancel", vp),
     ]
 
 
@@ -130,6 +135,8 @@ class LkKnnScoreArgs(C.Structure):
         ("d_pool", vp),
         ("pool_entries", C.c_int64),
         ("d_pool_cursor", vp),
+        ("user_mode", C.c_int32),
+        ("n_matrix_rows", C.c_int32),
     ]
 
 
@@ -154,6 +161,7 @@ SYMBOLS: dict[str, tuple] = {
     "lk_knn_build": (C.c_int, [C.POINTER(LkKnnBuildArgs), vp]),
     "lk_knn_merge_topk": (C.c_int, [C.POINTER(LkKnnBuildArgs), vp, vp, vp, vp]),
     "lk_knn_pool_to_csr": (C.c_int, [C.POINTER(LkKnnBuildArgs), vp, vp, vp, vp]),
+    "lk_knn_prep_columns": (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, vp, vp]),
     "lk_knn_score_warps": (C.c_int64, []),
     "lk_knn_score_batch": (C.c_int, [C.POINTER(LkKnnScoreArgs), vp]),
     "lk_topn_max": (C.c_int, []),

@@ -219,26 +219,40 @@ class ALSTrainerBase(ModelTrainer):
     kernel_events: list | None = None  # bench.py: (start, end) CUDA events around each row-solve launch
 
     def __init__(self, scorer: ALSBase, data, options: TrainingOptions):
+        from .prep import DeviceInteractions, coo_to_csr_pair
+
         self.scorer = scorer
-        ds = _as_dataset(data)
         self.device = _lib.require_device()
-        scorer.users = ds.users
-        scorer.items = ds.items
         self.rng = options.random_generator()
         k = self.config.embedding_size
+        if isinstance(data, DeviceInteractions):
+            # interactions already in HBM (scale-out configurations): R and Rᵀ are built on the device
+            # (prep.coo_to_csr_pair, the role of als/_common.py:216-219); there is no host copy
+            from .components import Vocabulary
 
-        coo = self.prepare_matrix(ds)
-        self.ui_host = InteractionCSR.from_scipy(coo)
-        self.iu_host = InteractionCSR.from_scipy(coo.T)
-        self.ui = engine.DeviceCSR.from_host(self.ui_host, self.device)
-        self.iu = engine.DeviceCSR.from_host(self.iu_host, self.device)
-        self.u_plan = engine.ALSHalfPlan.create(self.ui, k)
-        self.i_plan = engine.ALSHalfPlan.create(self.iu, k)
+            scorer.users = Vocabulary(np.arange(data.n_users), "user")
+            scorer.items = Vocabulary(np.arange(data.n_items), "item")
+            self.ui_host = self.iu_host = None
+            self.ui, self.iu, _ = coo_to_csr_pair(
+                data.users, data.items, self.prepare_values_device(data), data.n_users, data.n_items
+            )
+            n_users, n_items = data.n_users, data.n_items
+        else:
+            ds = _as_dataset(data)
+            scorer.users = ds.users
+            scorer.items = ds.items
+            coo = self.prepare_matrix(ds)
+            self.ui_host = InteractionCSR.from_scipy(coo)
+            self.iu_host = InteractionCSR.from_scipy(coo.T)
+            self.ui = engine.DeviceCSR.from_host(self.ui_host, self.device)
+            self.iu = engine.DeviceCSR.from_host(self.iu_host, self.device)
+            n_users, n_items = ds.user_count, ds.item_count
+        self._make_plans(k)
         self.otor_ws = engine.OtorWorkspace.create(k, self.device)
 
         # items first, then users, from one generator (als/_common.py:287-301)
-        q0 = self.initial_params(ds.item_count, k)
-        p0 = self.initial_params(ds.user_count, k)
+        q0 = self.initial_params(n_items, k)
+        p0 = self.initial_params(n_users, k)
         self.d_items = torch.from_numpy(q0).to(self.device)
         self.d_users = torch.from_numpy(p0).to(self.device)
         self.bf16 = self.config.gather_dtype == "bfloat16"
@@ -251,9 +265,23 @@ class ALSTrainerBase(ModelTrainer):
     def config(self):
         return self.scorer.config
 
+    def _chunk_nnz(self, k: int) -> int:
+        tcx = k == 64 and self.config.gather_dtype == "float32" or (
+            self.MODE == _lib.LK_ALS_IMPLICIT and getattr(self.config, "use_ratings", False)
+        )
+        return engine.TF32_CHUNK_NNZ if tcx else engine.DEFAULT_CHUNK_NNZ
+
+    def _make_plans(self, k: int) -> None:
+        c = self._chunk_nnz(k)
+        self.u_plan = engine.ALSHalfPlan.create(self.ui, k, c)
+        self.i_plan = engine.ALSHalfPlan.create(self.iu, k, c)
+
     # -- hooks -------------------------------------------------------------
     def prepare_matrix(self, data: Dataset):  # pragma: no cover
         raise NotImplementedError
+
+    def prepare_values_device(self, data) -> torch.Tensor:  # pragma: no cover
+        raise NotImplementedError("this trainer has no device-resident input path")
 
     def initial_params(self, nrows: int, ncols: int) -> np.ndarray:  # pragma: no cover
         raise NotImplementedError
@@ -453,6 +481,10 @@ class ImplicitMFTrainer(ALSTrainerBase):
         base = it.ratings if self.config.use_ratings else np.ones(it.nnz, dtype=np.float32)
         vals = (np.require(base, dtype=np.float32) * self.config.weight).astype(np.float32)
         return it.coo(vals)
+
+    def prepare_values_device(self, data) -> torch.Tensor:
+        base = data.ratings if self.config.use_ratings else torch.ones_like(data.ratings)
+        return (base.to(torch.float32) * float(self.config.weight)).to(torch.float32)
 
     def initial_params(self, nrows: int, ncols: int) -> np.ndarray:
         mat = self.rng.standard_normal((nrows, ncols), dtype=np.float32) * 0.01

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(AlsCfg<KP>::NT, AlsCfg<KP>::OCC) als_half_kern
     uint32_t phases = 0;
 
     for (;;) {
-        if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);
+        if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);
         __syncthreads();
         const int64_t ci = s_misc[0];
         __syncthreads();

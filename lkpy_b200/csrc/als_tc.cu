@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     if constexpr (PRELOAD) preload_otor();
 
     // the index of the next group is fetched one group ahead (during the solve phase)
-    if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);
+    if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);
     __syncthreads();
     for (;;) {
         const int64_t g = __shfl_sync(FULL, s_misc[0], 0);
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             // ------------------------------------------------------------------
             // phase 3': blocked Cholesky on the tensor cores, write-back
             // ------------------------------------------------------------------
-            if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);  // next group, read after the closing barrier
+            if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);  // next group, read after the closing barrier
             if (solve_mask) {
                 ctc::solve4<false, GJ>(tmem_base, yv, ws, solve_bar, solve_par, tid);
                 __syncthreads();  // pivot flags
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
         // ------------------------------------------------------------------
         // phase 3: per-warp Cholesky solve and write-back
         // ------------------------------------------------------------------
-        if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);  // next group, read after the closing barrier
+        if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);  // next group, read after the closing barrier
         if (active) {
             float *thisrow = a.d_this + (size_t)row * k;
             if (solve) {

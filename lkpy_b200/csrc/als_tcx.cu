@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(tcx::NT, 3) als_tcx_kernel(lk_als_args a)
     // byte offset of this lane's K-vector of feature 4*fq + j inside a tile: group (4fq+j)/8, row 4*rq.., core row (4fq+j)%8
     const uint32_t st_off = (uint32_t)((fq >> 1) * GROUP_STRIDE + rq * 128 + (fq & 1) * 64);
 
-    if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);
+    if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);
     __syncthreads();
     for (;;) {
         const int64_t g = __shfl_sync(FULL, s_misc[0], 0);
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(tcx::NT, 3) als_tcx_kernel(lk_als_args a)
         // ------------------------------------------------------------------
         // phase 3: blocked Cholesky on the tensor cores (chol_tc.cuh), write-back
         // ------------------------------------------------------------------
-        if (tid == 0) s_misc[0] = atomicAdd(a.d_work_counter, 1);  // next group, read after the closing barrier
+        if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);  // next group, read after the closing barrier
         if (solve_mask) {
             // old values of the rows about to be written: fetched before the solve so that the
             // write-back does not wait for them

@@ -119,6 +119,14 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// next work index from an atomic counter, or INT_MAX once the (optional) cancel flag is raised — the flag is
+// written by the host from another stream while the kernel runs, hence the uncached load
+__device__ __forceinline__ int fetch_work(int32_t *counter, const int32_t *cancel)
+{
+    if (cancel != nullptr && *reinterpret_cast<const volatile int32_t *>(cancel) != 0) return 0x7fffffff;
+    return atomicAdd(counter, 1);
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

@@ -22,9 +22,21 @@
 //
 // The work is HBM/L2-streaming integer+f32 scatter work (8 B per product), not
 // a GEMM: no tensor cores.  Layout: a CTA of W warps holds W sub-tiles (one
-// "column half" of the row); an item row takes n_halves passes.  Work items
-// (item, half) are pulled most-expensive-first from an atomic counter by a
-// persistent grid.
+// "column half" of the row); an item row takes n_halves passes.  Work units
+// (item, half, piece) are pulled most-expensive-first from an atomic counter by a
+// persistent grid; `piece` cuts the unit of a very expensive item into column
+// slices (piece p of P: the p-th P-th of every warp's sub-tile) so that one hot
+// item cannot keep a single CTA busy longer than a GPU's fair share of the whole
+// build — a column split leaves every dots[j] with its full ascending-user sum
+// (a user split would change the rounding).
+//
+// Ordering inside a warp: the products of up to 32 users are flattened over the
+// lanes in (user, column) order, so two lanes that hit the same column belong to
+// different users and the lower lane is the earlier user.  The groups of lanes
+// whose columns agree in their low 8 bits are found with one warp ballot per bit
+// (__match_any_sync itself was measured slower than the loop it replaced); round r
+// applies the r-th member of every group, so a batch takes 1-3 shared-memory
+// read-modify-write rounds instead of one round per user (~8).
 
 #include <algorithm>
 #include <cstdlib>
@@ -34,6 +46,7 @@
 namespace lk {
 
 constexpr uint32_t SENT = 0xffffffffu;  // "never touched" accumulator marker (a NaN no product yields)
+constexpr int KEY_BITS = 8;             // column bits compared when grouping the lanes of a batch
 constexpr int HIST_BINS = 2048;
 
 __device__ __forceinline__ bool is_cand(uint32_t bits, float min_sim)
@@ -167,7 +180,7 @@ __global__ void __launch_bounds__(W * 32, 1024 / (W * 32)) knn_build_kernel(lk_k
     constexpr int NT = W * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const lk_knn_geom &g = a.geom;
-    const int TW = g.tile_cols, H = g.n_halves, S1 = g.n_subtiles + 1;
+    const int TW = g.tile_cols, S1 = g.n_subtiles + 1;
     const int CW = W * TW;
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);       // [CW] f32 bit patterns
     uint32_t *hist = acc + CW;                                     // [HIST_BINS]
@@ -183,25 +196,29 @@ __global__ void __launch_bounds__(W * 32, 1024 / (W * 32)) knn_build_kernel(lk_k
     for (int idx = tid; idx < CW; idx += NT) acc[idx] = SENT;
     __syncthreads();
 
-    const int64_t n_work = a.n_work * H;
+    const int64_t n_work = a.n_work;
     for (;;) {
-        if (tid == 0) bc[8] = atomicAdd(a.d_work_counter, 1);
+        if (tid == 0) bc[8] = fetch_work(a.d_work_counter, a.d_cancel);
         __syncthreads();
         const int64_t wi = bc[8];
         __syncthreads();
         if (wi >= n_work) break;
-        const int item = a.d_order[wi / H];
-        const int h = (int)(wi % H);
+        const int uid = a.d_sched[wi];
+        const int4 un = __ldg(reinterpret_cast<const int4 *>(a.d_units) + uid);
+        const int item = un.x, h = un.y;
+        const int pw = TW / un.w;  // columns of this piece inside every warp's sub-tile
 
         // ------------------------------------------------------------------
-        // accumulate: warp `warp` owns columns [col0, col0 + TW)
+        // accumulate: warp `warp` owns columns [col0, col0 + TW), of which this unit covers [jlo, jhi)
         // ------------------------------------------------------------------
         {
             const int s = h * W + warp;
             const int col0 = s * TW;
+            const int jlo = un.z * pw, jhi = jlo + pw;
             uint32_t *my = acc + warp * TW;
             const int iu0 = a.d_iu_indptr[item];
             const int m = a.d_iu_indptr[item + 1] - iu0;
+            const unsigned lt_mask = (1u << lane) - 1u;
             for (int t0 = 0; t0 < m; t0 += 32) {
                 int len = 0, base = 0;
                 float r = 0.0f;
@@ -234,20 +251,29 @@ __global__ void __launch_bounds__(W * 32, 1024 / (W * 32)) knn_build_kernel(lk_k
                         const float val = __ldg(a.d_ui_vals + src);
                         prod = __fmul_rn(rq, val);  // never contracted (item_train.rs:128)
                         j = col - col0;
-                        valid = col != item;  // diagonal excluded by index (item_train.rs:120-122)
+                        // diagonal excluded by index (item_train.rs:120-122); columns of other pieces are not ours
+                        valid = col != item && j >= jlo && j < jhi;
                     }
-                    unsigned pend = __ballot_sync(FULL, valid);
-                    while (pend) {  // users in ascending order; one user's lanes hit distinct columns
-                        const int leader = __ffs(pend) - 1;
-                        const int qq = __shfl_sync(FULL, q, leader);
-                        const bool mine = valid && q == qq;
-                        if (mine) {
+                    // lanes are in (user, column) order: lanes that share a column are different users, the
+                    // lower lane the earlier one.  Lanes whose columns agree in their low KEY_BITS bits are found
+                    // with one ballot per bit (a superset of the true same-column groups: a false member only
+                    // costs a round, never the order); round rr applies the rr-th member of every group.
+                    unsigned peers = __ballot_sync(FULL, valid);
+#pragma unroll
+                    for (int b = 0; b < KEY_BITS; b++) {
+                        const bool bit = (j >> b) & 1;
+                        const unsigned mb = __ballot_sync(FULL, bit);
+                        peers &= bit ? mb : ~mb;
+                    }
+                    const int rank = __popc(peers & lt_mask);
+                    const int rounds = __reduce_max_sync(FULL, valid ? rank : 0);
+                    for (int rr = 0; rr <= rounds; rr++) {
+                        if (valid && rank == rr) {
                             const uint32_t old = my[j];
                             const float b = old == SENT ? 0.0f : __uint_as_float(old);
                             my[j] = __float_as_uint(__fadd_rn(b, prod));
                         }
                         __syncwarp();
-                        pend &= ~__ballot_sync(FULL, mine);
                     }
                 }
             }
@@ -258,7 +284,7 @@ __global__ void __launch_bounds__(W * 32, 1024 / (W * 32)) knn_build_kernel(lk_k
         // epilogue: threshold, (top-K | all), emit, reset accumulators
         // ------------------------------------------------------------------
         const int half_col0 = h * CW;
-        const int64_t pidx = (int64_t)item * H + h;
+        const int64_t pidx = uid;  // partial lists / pool segments are indexed by unit
         // candidate count
         int local = 0;
         for (int idx = tid; idx < CW; idx += NT) local += is_cand(acc[idx], min_sim) ? 1 : 0;
@@ -417,8 +443,8 @@ __global__ void __launch_bounds__(128) knn_merge_kernel(lk_knn_build_args a, int
                                                        int32_t *__restrict__ out_cnt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int H = a.geom.n_halves, K = a.save_nbrs;
-    const int cap = H * K;
+    const int K = a.save_nbrs;
+    const int cap = a.max_units_per_item * K;
     int32_t *cols = reinterpret_cast<int32_t *>(smem_raw);
     float *sims = reinterpret_cast<float *>(cols + cap);
     int32_t *fus = reinterpret_cast<int32_t *>(sims + cap);
@@ -426,9 +452,10 @@ __global__ void __launch_bounds__(128) knn_merge_kernel(lk_knn_build_args a, int
     __shared__ int s_n, s_gt, s_keep;
     const int tid = threadIdx.x;
     for (int item = blockIdx.x; item < a.geom.n_items; item += gridDim.x) {
+        const int u0 = a.d_unit_ptr[item], u1 = a.d_unit_ptr[item + 1];
         if (tid == 0) {
             int n = 0;
-            for (int h = 0; h < H; h++) n += a.d_part_cnt[(int64_t)item * H + h];
+            for (int u = u0; u < u1; u++) n += a.d_part_cnt[u];
             s_n = n;
             s_keep = 0;
         }
@@ -437,11 +464,11 @@ __global__ void __launch_bounds__(128) knn_merge_kernel(lk_knn_build_args a, int
         // gather
         {
             int off = 0;
-            for (int h = 0; h < H; h++) {
-                const int c = a.d_part_cnt[(int64_t)item * H + h];
+            for (int u = u0; u < u1; u++) {
+                const int c = a.d_part_cnt[u];
                 for (int t = tid; t < c; t += blockDim.x) {
-                    cols[off + t] = a.d_part_cols[((int64_t)item * H + h) * K + t];
-                    sims[off + t] = a.d_part_vals[((int64_t)item * H + h) * K + t];
+                    cols[off + t] = a.d_part_cols[(int64_t)u * K + t];
+                    sims[off + t] = a.d_part_vals[(int64_t)u * K + t];
                 }
                 off += c;
             }
@@ -504,14 +531,14 @@ __global__ void __launch_bounds__(128) knn_merge_kernel(lk_knn_build_args a, int
 __global__ void pool_to_csr_kernel(lk_knn_build_args a, const int64_t *__restrict__ out_indptr,
                                    int32_t *__restrict__ out_cols, float *__restrict__ out_vals)
 {
-    const int H = a.geom.n_halves;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < a.geom.n_items; item += warps) {
         int64_t dst = out_indptr[item];
-        for (int h = 0; h < H; h++) {
-            const int64_t src = a.d_pool_off[(int64_t)item * H + h];
-            const int c = a.d_part_cnt[(int64_t)item * H + h];
+        // unbounded mode has one unit per (item, half), in column order
+        for (int u = a.d_unit_ptr[item]; u < a.d_unit_ptr[item + 1]; u++) {
+            const int64_t src = a.d_pool_off[u];
+            const int c = a.d_part_cnt[u];
             for (int t = lane; t < c; t += 32) {
                 out_cols[dst + t] = a.d_pool_cols[src + t];
                 out_vals[dst + t] = a.d_pool_vals[src + t];
@@ -586,8 +613,7 @@ int lk_knn_row_cost(const lk_knn_geom *geom, const int32_t *d_ui_indptr, const i
 static int64_t knn_grid(const lk_knn_geom &g, int64_t n_work)
 {
     int64_t grid = (int64_t)sm_count() * g.ctas_per_sm;
-    const int64_t total = n_work * g.n_halves;
-    if (grid > total) grid = total;
+    if (grid > n_work) grid = n_work;
     return grid < 1 ? 1 : grid;
 }
 
@@ -603,8 +629,8 @@ int lk_knn_build(const lk_knn_build_args *args, void *stream)
     const lk_knn_build_args &a = *args;
     const lk_knn_geom &g = a.geom;
     LK_REQUIRE(a.d_ui_indptr && a.d_ui_cols && a.d_ui_vals && a.d_iu_indptr && a.d_iu_cols &&
-                   a.d_iu_vals && a.d_tile_ptr && a.d_order && a.d_work_counter && a.d_status &&
-                   a.d_part_cnt && a.d_tie_scratch,
+                   a.d_iu_vals && a.d_tile_ptr && a.d_units && a.d_unit_ptr && a.d_sched && a.d_work_counter &&
+                   a.d_status && a.d_part_cnt && a.d_tie_scratch,
                LK_ERR_INVALID, "lk_knn_build: null pointer");
     if (a.save_nbrs > 0)
         LK_REQUIRE(a.d_part_cols && a.d_part_vals, LK_ERR_INVALID, "truncated build needs partial lists");
@@ -642,9 +668,10 @@ int lk_knn_merge_topk(const lk_knn_build_args *args, int32_t *d_out_cols, float 
     LK_REQUIRE(args && d_out_cols && d_out_vals && d_out_cnt, LK_ERR_INVALID, "lk_knn_merge_topk: null");
     const lk_knn_build_args &a = *args;
     LK_REQUIRE(a.save_nbrs > 0, LK_ERR_INVALID, "merge is for the truncated build");
-    const int cap = a.geom.n_halves * a.save_nbrs;
+    LK_REQUIRE(a.d_unit_ptr && a.max_units_per_item >= 1, LK_ERR_INVALID, "lk_knn_merge_topk: no unit table");
+    const int cap = a.max_units_per_item * a.save_nbrs;
     const int smem = cap * 16;
-    LK_REQUIRE(smem <= 200 * 1024, LK_ERR_UNSUPPORTED, "n_halves*save_nbrs = %d too large to merge", cap);
+    LK_REQUIRE(smem <= 200 * 1024, LK_ERR_UNSUPPORTED, "units per item * save_nbrs = %d too large to merge", cap);
     LK_CUDA_TRY(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = std::min(a.geom.n_items, sm_count() * 16);
     if (grid < 1) grid = 1;

@@ -115,9 +115,10 @@ __device__ void rescore_exact(const lk_knn_score_args &a, int64_t r0, int64_t r1
     int len = 0;
     int is_heap = 0;
     const int limit = a.max_nbrs;
+    const int n_rows = a.user_mode ? a.n_matrix_rows : a.n_items;
     for (int64_t p = r0; p < r1; p++) {
         const int r = a.d_ref_items[p];
-        if (r < 0 || r >= a.n_items) continue;
+        if (r < 0 || r >= n_rows) continue;
         int64_t lo = a.d_sim_indptr[r], hi = a.d_sim_indptr[r + 1];
         const int64_t end = hi;
         while (lo < hi) {
@@ -125,9 +126,10 @@ __device__ void rescore_exact(const lk_knn_score_args &a, int64_t r0, int64_t r1
             if (a.d_sim_cols[mid] < t) lo = mid + 1; else hi = mid;
         }
         if (lo >= end || a.d_sim_cols[lo] != t) continue;
+        const float mv = a.d_sim_vals ? a.d_sim_vals[lo] : 0.0f, hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
         AccEnt e;
-        e.w = a.d_sim_vals[lo];
-        e.v = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
+        e.w = a.user_mode ? hv : mv;
+        e.v = a.user_mode ? mv : hv;
         acc_push(d, len, is_heap, e, limit);
     }
     float tw = 0.0f, ws = 0.0f;
@@ -144,7 +146,12 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gwarp >= a.slotmap_warps) return;  // one slot-map row per working warp
     int32_t *slotmap = a.d_slotmap + (size_t)gwarp * a.n_items;
-    const bool explicit_fb = a.d_ref_vals != nullptr;
+    // item mode: weight = similarity entry, value = the history entry's rating (item_score.rs:22-111);
+    // user mode (user_score.rs:21-98): weight = the history entry's value (the neighbour's similarity),
+    // value = the matrix entry (the neighbour's rating of the item)
+    const bool user_mode = a.user_mode != 0;
+    const int n_rows = user_mode ? a.n_matrix_rows : a.n_items;
+    const bool explicit_fb = user_mode ? a.d_sim_vals != nullptr : a.d_ref_vals != nullptr;
     const float qnan = __int_as_float(0x7fc00000);
     const int hwords = heap_state_words(a.max_nbrs);
     uint32_t *heap_base = a.d_heap_scratch != nullptr
@@ -173,14 +180,15 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
         // 2. contributions in history order; one similarity row's entries hit distinct targets
         for (int64_t p = r0; p < r1; p++) {
             const int r = a.d_ref_items[p];
-            if (r < 0 || r >= a.n_items) continue;  // null reference item
-            const float rv = explicit_fb ? a.d_ref_vals[p] : 0.0f;
+            if (r < 0 || r >= n_rows) continue;  // null reference item
+            const float hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
             const int64_t s0 = a.d_sim_indptr[r], s1 = a.d_sim_indptr[r + 1];
             for (int64_t e = s0 + lane; e < s1; e += 32) {
                 const int t = a.d_sim_cols[e];
                 const int32_t slot = slotmap[t];
                 if (slot >= 0) {
-                    const float sim = a.d_sim_vals[e];
+                    const float mv = a.d_sim_vals ? a.d_sim_vals[e] : 0.0f;
+                    const float sim = user_mode ? hv : mv, rv = user_mode ? mv : hv;
                     if (sim != sim) atomicCAS(a.d_status, 0, 2);  // "similarity is null" (accum.rs:146-152)
                     const int64_t x = t0 + slot;
                     const int c = a.d_acc_cnt[x];
@@ -218,8 +226,8 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
             if (n_tracked > 0) {
                 for (int64_t p = r0; p < r1; p++) {
                     const int r = a.d_ref_items[p];
-                    if (r < 0 || r >= a.n_items) continue;
-                    const float rv = explicit_fb ? a.d_ref_vals[p] : 0.0f;
+                    if (r < 0 || r >= n_rows) continue;
+                    const float hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
                     const int64_t s0 = a.d_sim_indptr[r], s1 = a.d_sim_indptr[r + 1];
                     for (int64_t e = s0 + lane; e < s1; e += 32) {
                         const int32_t slot = slotmap[a.d_sim_cols[e]];
@@ -228,9 +236,10 @@ __global__ void __launch_bounds__(256) knn_score_kernel(lk_knn_score_args a)
                         if (mk > -2) continue;
                         uint32_t *hs = heap_base + (size_t)(-mk - 2) * hwords;
                         int len = (int)hs[0], is_heap = (int)hs[1];
+                        const float mv = a.d_sim_vals ? a.d_sim_vals[e] : 0.0f;
                         AccEnt ent;
-                        ent.w = a.d_sim_vals[e];
-                        ent.v = rv;
+                        ent.w = user_mode ? hv : mv;
+                        ent.v = user_mode ? mv : hv;
                         acc_push(reinterpret_cast<AccEnt *>(hs + 2), len, is_heap, ent, a.max_nbrs);
                         hs[0] = (uint32_t)len, hs[1] = (uint32_t)is_heap;
                     }
@@ -295,7 +304,9 @@ __global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args 
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gwarp >= a.slotmap_warps) return;  // one slot-map row per working warp
     int32_t *slotmap = a.d_slotmap + (size_t)gwarp * a.n_items;
-    const bool explicit_fb = a.d_ref_vals != nullptr;
+    const bool user_mode = a.user_mode != 0;  // see knn_score_kernel
+    const int n_rows = user_mode ? a.n_matrix_rows : a.n_items;
+    const bool explicit_fb = user_mode ? a.d_sim_vals != nullptr : a.d_ref_vals != nullptr;
     const float qnan = __int_as_float(0x7fc00000);
     int32_t *acc_cnt = a.d_acc_cnt;
     int32_t *acc_off = reinterpret_cast<int32_t *>(a.d_acc_ws);  // list offset of a target (scratch reuse)
@@ -336,15 +347,16 @@ __global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args 
             const int64_t p = p0 + lane;
             if (p < r1) {
                 const int r = a.d_ref_items[p];
-                if (r >= 0 && r < a.n_items) {
+                if (r >= 0 && r < n_rows) {
                     const int64_t s1 = a.d_sim_indptr[r + 1];
                     for (int64_t e = a.d_sim_indptr[r]; e < s1; e += UB) {  // UB entries of the row in flight
                         int cc[UB], sl[UB];
                         float sv[UB];
+                        const float hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
 #pragma unroll
                         for (int u = 0; u < UB; u++) {
                             cc[u] = e + u < s1 ? __ldg(a.d_sim_cols + e + u) : -1;
-                            sv[u] = e + u < s1 ? __ldg(a.d_sim_vals + e + u) : 0.0f;
+                            sv[u] = user_mode ? hv : ((e + u < s1 && a.d_sim_vals) ? __ldg(a.d_sim_vals + e + u) : 0.0f);
                         }
 #pragma unroll
                         for (int u = 0; u < UB; u++) sl[u] = cc[u] >= 0 ? slotmap[cc[u]] : -1;
@@ -394,16 +406,16 @@ __global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args 
                 const int64_t p = p0 + lane;
                 if (p < r1) {
                     const int r = a.d_ref_items[p];
-                    if (r >= 0 && r < a.n_items) {
-                        const float rv = explicit_fb ? a.d_ref_vals[p] : 0.0f;
+                    if (r >= 0 && r < n_rows) {
+                        const float hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
                         const int64_t s1 = a.d_sim_indptr[r + 1];
                         for (int64_t e = a.d_sim_indptr[r]; e < s1; e += UB) {
                             int cc[UB], sl[UB], of[UB], kp[UB];
-                            float sv[UB];
+                            float sv[UB];  // the matrix entry's value
 #pragma unroll
                             for (int u = 0; u < UB; u++) {
                                 cc[u] = e + u < s1 ? __ldg(a.d_sim_cols + e + u) : -1;
-                                sv[u] = e + u < s1 ? __ldg(a.d_sim_vals + e + u) : 0.0f;
+                                sv[u] = (e + u < s1 && a.d_sim_vals) ? __ldg(a.d_sim_vals + e + u) : 0.0f;
                             }
 #pragma unroll
                             for (int u = 0; u < UB; u++) sl[u] = cc[u] >= 0 ? slotmap[cc[u]] : -1;
@@ -417,8 +429,8 @@ __global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args 
                                 if (sl[u] >= 0) {
                                     PoolEnt ent;
                                     ent.pos = (int32_t)(p - r0);
-                                    ent.sim = sv[u];
-                                    ent.rv = rv;
+                                    ent.sim = user_mode ? hv : sv[u];
+                                    ent.rv = user_mode ? sv[u] : hv;
                                     ent.pad = 0;
                                     pool[base + (unsigned long long)(of[u] + kp[u])] = ent;
                                 }
@@ -537,10 +549,12 @@ int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
     LK_REQUIRE(a.n_items >= 1 && a.n_queries >= 0, LK_ERR_INVALID, "bad shape");
     LK_REQUIRE(a.max_nbrs >= 1 && a.max_nbrs <= SCORE_MAX_NBRS, LK_ERR_UNSUPPORTED,
                "max_nbrs must be in 1..%d", SCORE_MAX_NBRS);
-    LK_REQUIRE(a.d_sim_indptr && a.d_sim_cols && a.d_sim_vals && a.d_ref_indptr && a.d_ref_items &&
+    LK_REQUIRE(a.d_sim_indptr && a.d_sim_cols && a.d_ref_indptr && a.d_ref_items &&
                    a.d_tgt_indptr && a.d_tgt_items && a.d_slotmap && a.d_acc_ws && a.d_acc_tw &&
                    a.d_acc_cnt && a.d_scores && a.d_counts && a.d_work_counter && a.d_status,
                LK_ERR_INVALID, "lk_knn_score_batch: null pointer");
+    LK_REQUIRE(a.user_mode ? a.d_ref_vals != nullptr : a.d_sim_vals != nullptr, LK_ERR_INVALID,
+               "lk_knn_score_batch: the weights (similarities) are missing");
     LK_REQUIRE(a.slotmap_warps >= 1, LK_ERR_INVALID, "slotmap too small");
     if (a.n_queries == 0) return LK_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

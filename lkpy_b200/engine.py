@@ -20,6 +20,10 @@ from ._lib import LkAlsArgs, LkKnnBuildArgs, LkKnnGeom, LkKnnScoreArgs, check, l
 from .data import InteractionCSR
 
 DEFAULT_CHUNK_NNZ = 4096
+#: rows of the fp32 / weighted tensor-core path (als_tcx.cu) are cut shorter: a tcgen05 accumulator adds with
+#: round-toward-zero, three times per 8 gathered rows on that path, so the error of a partial Gram grows with
+#: its length (measured ~2.3e-8 relative per nonzero); parts are summed with round-to-nearest by the CUDA cores
+TF32_CHUNK_NNZ = 1024
 #: engine limits the reference does not have: validated up front by the configs
 ALS_MAX_FEATURES = 128
 KNN_SCORE_MAX_NBRS = 128
@@ -164,6 +168,7 @@ def als_half_epoch(
     reg: float = 0.0,
     replicas: list[torch.Tensor] | None = None,
     replica_row0: int = 0,
+    cancel: torch.Tensor | None = None,
 ) -> None:
     """
     Enqueue one half-epoch.  ``this`` [n_rows,k] f32 is updated in place;
@@ -206,6 +211,7 @@ def als_half_epoch(
     a.vals_uniform = 1 if plan.vals_uniform else 0
     a.uniform_val = plan.uniform_val
     a.d_prof = ptr(PROF_BUFFER)
+    a.d_cancel = ptr(cancel)  # optional device flag: non-zero stops the hand-out of rows (cooperative cancel)
     check(lib().lk_als_half_epoch(C.byref(a), stream_ptr()), "lk_als_half_epoch")
 
 
@@ -216,7 +222,7 @@ def als_half_epoch(
 
 @dataclass
 class KnnBuildPlan:
-    """Tiling, tile pointers and cost-ordered work list for one (UI, IU) pair."""
+    """Tiling, tile pointers and cost-ordered work units for one (UI, IU) pair."""
 
     ui: DeviceCSR
     iu: DeviceCSR
@@ -228,9 +234,13 @@ class KnnBuildPlan:
     work_counter: torch.Tensor
     status: torch.Tensor
     extra: dict = field(default_factory=dict)
+    world: int = 1  # GPUs sharing the build: sets how finely hot items are cut into column pieces
+    MAX_PIECES = 8
+    #: a piece repeats the unit's loads and does 1/P of its shared-memory updates: modelled cost share of the loads
+    LOAD_SHARE = 0.45
 
     @classmethod
-    def create(cls, ui: DeviceCSR, iu: DeviceCSR) -> "KnnBuildPlan":
+    def create(cls, ui: DeviceCSR, iu: DeviceCSR, world: int = 1) -> "KnnBuildPlan":
         L = lib()
         dev = ui.indptr.device
         n_users, n_items = ui.shape
@@ -244,12 +254,13 @@ class KnnBuildPlan:
             ui, iu, g, tile_ptr, cost, torch.empty(0, dtype=torch.int32, device=dev), tie,
             torch.zeros(1, dtype=torch.int32, device=dev),
             torch.zeros(1, dtype=torch.int32, device=dev),
+            world=max(1, int(world)),
         )  # fmt: skip
         plan.prepare()
         return plan
 
     def prepare(self) -> None:
-        """(Re)compute tile pointers, row costs and the cost-ordered work list into the plan's buffers."""
+        """(Re)compute tile pointers, row costs, the cost-ordered item list and the work units."""
         L = lib()
         g = self.geom
         check(
@@ -265,21 +276,75 @@ class KnnBuildPlan:
             "lk_knn_row_cost",
         )
         self.order = torch.argsort(self.cost, descending=True, stable=True).to(torch.int32)
+        self.extra.pop("units", None)
 
-    def _args(self, order: torch.Tensor, min_sim: float, save_nbrs: int) -> LkKnnBuildArgs:
+    def units(self, split_hot: bool):
+        """
+        Work units {item, half, piece, n_pieces}, item-major, with their schedule (most expensive first).
+        ``split_hot`` (truncated build only): an (item, half) unit whose product count exceeds half a
+        CTA's fair share of the whole build on ``world`` GPUs is cut into 2 / 4 / 8 column pieces
+        (``knn_build.cu``) — without it the five hottest ML-25M-shaped items pin one CTA each for longer
+        than an 8-GPU build should take.  No host sync: everything is computed on the device.
+        """
+        key = ("units", bool(split_hot))
+        cached = self.extra.get("units")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        dev = self.cost.device
+        H, n_items = self.geom.n_halves, self.geom.n_items
+        cost = self.cost.to(torch.float64)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        n_cta = sms * self.geom.ctas_per_sm * self.world
+        pieces = torch.ones(n_items, dtype=torch.int64, device=dev)
+        if split_hot:
+            fair = cost.sum() / n_cta  # products per CTA if the build were perfectly balanced
+            want = (cost / H) / (0.5 * fair).clamp_min(1.0)
+            pieces = torch.where(want > 4, 8, torch.where(want > 2, 4, torch.where(want > 1, 2, 1))).to(torch.int64)
+            pieces = pieces.clamp_max(self.MAX_PIECES)
+        per_item = pieces * H
+        unit_ptr = torch.zeros(n_items + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(per_item, 0, out=unit_ptr[1:])
+        item_of = torch.repeat_interleave(torch.arange(n_items, device=dev), per_item)
+        local = torch.arange(item_of.numel(), device=dev) - unit_ptr[item_of]
+        p_of = pieces[item_of]
+        units = torch.stack([item_of, local // p_of, local % p_of, p_of], dim=1).to(torch.int32).contiguous()
+        ucost = (cost[item_of] / H) * (self.LOAD_SHARE + (1.0 - self.LOAD_SHARE) / p_of.to(torch.float64))
+        sched = torch.argsort(ucost, descending=True, stable=True).to(torch.int32)
+        out = {
+            "units": units, "unit_ptr": unit_ptr.to(torch.int32), "sched": sched, "item_of": item_of,
+            "max_units": int(H * (self.MAX_PIECES if split_hot else 1)), "n_units": int(units.shape[0]),
+        }  # fmt: skip
+        self.extra["units"] = (key, out)
+        return out
+
+    #: optional device int32 flag checked by the build kernel whenever a CTA fetches a work unit
+    cancel: torch.Tensor | None = None
+
+    def _args(self, u: dict, sched: torch.Tensor, min_sim: float, save_nbrs: int) -> LkKnnBuildArgs:
         a = LkKnnBuildArgs()
+        a.d_cancel = ptr(self.cancel)
         a.geom = self.geom
         a.d_ui_indptr, a.d_ui_cols, a.d_ui_vals = ptr(self.ui.indptr), ptr(self.ui.indices), ptr(self.ui.values)
         a.d_iu_indptr, a.d_iu_cols, a.d_iu_vals = ptr(self.iu.indptr), ptr(self.iu.indices), ptr(self.iu.values)
         a.d_tile_ptr = ptr(self.tile_ptr)
-        a.d_order = ptr(order)
-        a.n_work = order.numel()
+        a.d_units, a.d_unit_ptr, a.max_units_per_item = ptr(u["units"]), ptr(u["unit_ptr"]), u["max_units"]
+        a.d_sched = ptr(sched)
+        a.n_work = sched.numel()
         a.min_sim = float(np.float32(min_sim))
         a.save_nbrs = int(save_nbrs)
         a.d_tie_scratch = ptr(self.tie_scratch)
         a.d_work_counter = ptr(self.work_counter)
         a.d_status = ptr(self.status)
         return a
+
+    def _sched_for(self, u: dict, order: torch.Tensor | None) -> torch.Tensor:
+        """The schedule restricted to the units of the items in ``order`` (item-sharded build)."""
+        if order is None:
+            return u["sched"]
+        mine = torch.zeros(self.geom.n_items, dtype=torch.bool, device=order.device)
+        mine[order.long()] = True
+        sched = u["sched"]
+        return sched[mine[u["item_of"][sched.long()]]].contiguous()
 
     def build_topk(
         self, min_sim: float, save_nbrs: int, order: torch.Tensor | None = None
@@ -290,25 +355,26 @@ class KnnBuildPlan:
         """
         L = lib()
         dev = self.ui.indptr.device
-        n_items, H, K = self.geom.n_items, self.geom.n_halves, int(save_nbrs)
-        if H * K * 16 > KNN_MERGE_SMEM_LIMIT:  # checked before the build runs, not after it
+        n_items, K = self.geom.n_items, int(save_nbrs)
+        u = self.units(split_hot=True)
+        if u["max_units"] * K * 16 > KNN_MERGE_SMEM_LIMIT:  # checked before the build runs, not after it
             raise _lib.EngineError(
-                f"save_nbrs={K} with {H} column blocks exceeds the merge limit "
-                f"(n_halves * save_nbrs <= {KNN_MERGE_SMEM_LIMIT // 16}); use save_nbrs=None"
+                f"save_nbrs={K} with {u['max_units']} work units per item exceeds the merge limit "
+                f"(units * save_nbrs <= {KNN_MERGE_SMEM_LIMIT // 16}); use save_nbrs=None"
             )
-        order = self.order if order is None else order.to(torch.int32).contiguous()
-        ws = self.extra.get(("topk", K))
+        sched = self._sched_for(u, order)
+        ws = self.extra.get(("topk", K, u["n_units"]))
         if ws is None:  # workspaces are allocated once per plan and K, reused by every build
             ws = (
-                torch.empty(n_items * H * K, dtype=torch.int32, device=dev),
-                torch.empty(n_items * H * K, dtype=torch.float32, device=dev),
-                torch.empty(n_items * H, dtype=torch.int32, device=dev),
+                torch.empty(u["n_units"] * K, dtype=torch.int32, device=dev),
+                torch.empty(u["n_units"] * K, dtype=torch.float32, device=dev),
+                torch.empty(u["n_units"], dtype=torch.int32, device=dev),
             )
-            self.extra[("topk", K)] = ws
+            self.extra[("topk", K, u["n_units"])] = ws
         part_cols, part_vals, part_cnt = ws
         part_cnt.zero_()
         self.status.zero_()
-        a = self._args(order, min_sim, K)
+        a = self._args(u, sched, min_sim, K)
         a.d_part_cols, a.d_part_vals, a.d_part_cnt = ptr(part_cols), ptr(part_vals), ptr(part_cnt)
         check(L.lk_knn_build(C.byref(a), stream_ptr()), "lk_knn_build")
         out_cols = torch.empty((n_items, K), dtype=torch.int32, device=dev)
@@ -327,10 +393,12 @@ class KnnBuildPlan:
         L = lib()
         dev = self.ui.indptr.device
         n_items, H = self.geom.n_items, self.geom.n_halves
-        order = self.order if order is None else order.to(torch.int32).contiguous()
+        u = self.units(split_hot=False)  # one unit per (item, half): pool segments stay in column order
+        sched = self._sched_for(u, order)
+        rows = self.order if order is None else order.to(torch.int32).contiguous()
         if capacity is None:
             # every kept pair shares a user: at most sum of the processed rows' product counts
-            capacity = int(min(int(self.cost[order.long()].sum().item()), order.numel() * max(n_items - 1, 1)))
+            capacity = int(min(int(self.cost[rows.long()].sum().item()), rows.numel() * max(n_items - 1, 1)))
         capacity = max(capacity, 1)
         pool_cols = torch.empty(capacity, dtype=torch.int32, device=dev)
         pool_vals = torch.empty(capacity, dtype=torch.float32, device=dev)
@@ -338,7 +406,7 @@ class KnnBuildPlan:
         part_cnt = torch.zeros(n_items * H, dtype=torch.int32, device=dev)
         cursor = torch.zeros(1, dtype=torch.int64, device=dev)
         self.status.zero_()
-        a = self._args(order, min_sim, 0)
+        a = self._args(u, sched, min_sim, 0)
         a.d_part_cnt = ptr(part_cnt)
         a.d_pool_cols, a.d_pool_vals, a.pool_capacity = ptr(pool_cols), ptr(pool_vals), capacity
         a.d_pool_off, a.d_pool_cursor = ptr(pool_off), ptr(cursor)
@@ -382,13 +450,17 @@ class KnnScorerState:
     n_items: int
     sim_indptr: torch.Tensor  # int64
     sim_cols: torch.Tensor
-    sim_vals: torch.Tensor
+    sim_vals: torch.Tensor | None  # None: user mode with implicit feedback (structure only)
     max_warps: int
     work_counter: torch.Tensor
     status: torch.Tensor
     slotmap: torch.Tensor | None = None  # [warps, n_items] int32, all -1 between calls; grown on demand
     heap_scratch: dict = field(default_factory=dict)  # (max_nbrs, warps) -> per-warp heap states
     lock: object = field(default_factory=threading.Lock)  # the mutable device state above is per-state
+    #: user-kNN scoring (user_score.rs:21-98): the matrix is users x items ratings, a query's "history" is its
+    #: neighbour list and carries the weights (lk_knn_score_args.user_mode)
+    user_mode: bool = False
+    n_rows: int = 0
     HEAP_TARGETS_PER_WARP = 2048
     USE_LISTS = True  # list-based kernel (parallel over the history); False: the sequential kernel
 
@@ -416,7 +488,9 @@ class KnnScorerState:
         return t, per_warp
 
     @classmethod
-    def create(cls, n_items: int, indptr, cols, vals, device=None) -> "KnnScorerState":
+    def create(cls, n_items: int, indptr, cols, vals, device=None, user_mode: bool = False) -> "KnnScorerState":
+        """``n_items`` = number of columns (targets).  Item mode: the square similarity matrix; user mode: the
+        users x items (centred) rating matrix, ``vals`` None for implicit feedback."""
         device = device or _lib.require_device()
         warps = int(lib().lk_knn_score_warps())
 
@@ -424,14 +498,17 @@ class KnnScorerState:
             t = torch.as_tensor(t)
             return t.to(device=device, dtype=dt).contiguous()
 
+        ip = dev(indptr, torch.int64)
         return cls(
             n_items,
-            dev(indptr, torch.int64),
+            ip,
             dev(cols, torch.int32),
-            dev(vals, torch.float32),
+            None if vals is None else dev(vals, torch.float32),
             warps,
             torch.zeros(1, dtype=torch.int32, device=device),
             torch.zeros(1, dtype=torch.int32, device=device),
+            user_mode=bool(user_mode),
+            n_rows=int(ip.numel() - 1),
         )
 
     def score(
@@ -472,13 +549,15 @@ class KnnScorerState:
         a.d_acc_ws, a.d_acc_tw, a.d_acc_cnt = ptr(acc_ws), ptr(acc_tw), ptr(acc_cnt)
         a.d_scores, a.d_counts = ptr(scores), ptr(counts)
         a.d_work_counter, a.d_status = ptr(self.work_counter), ptr(self.status)
+        a.user_mode, a.n_matrix_rows = (1 if self.user_mode else 0), self.n_rows
+        n_rows = self.n_rows if self.user_mode else self.n_items
         use_lists = self.USE_LISTS and ref_items.numel() > 0 and _lib.get_option("LK_KNN_SCORE_SEQ") != 1
         if use_lists:
             # contribution pool for the list-based kernel: one 16-byte entry per (reference item,
             # similarity-row entry) pair of the batch
             r = ref_items.long()
-            ok = (r >= 0) & (r < self.n_items)
-            rr = r.clamp(0, self.n_items - 1)
+            ok = (r >= 0) & (r < n_rows)
+            rr = r.clamp(0, n_rows - 1)
             total = int(((self.sim_indptr[rr + 1] - self.sim_indptr[rr]) * ok).sum().item())
             pool = self.heap_scratch.get("pool")
             if pool is None or pool.numel() < 4 * max(total, 1):

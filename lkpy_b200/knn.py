@@ -31,6 +31,8 @@ class ItemKNNConfig(BaseModel, extra="forbid"):
     save_nbrs: PositiveInt | None = None
     feedback: Literal["explicit", "implicit"] = "explicit"
     block_size: int = 250  # accepted and ignored, as in the reference
+    prep: Literal["device", "host"] = "device"
+    "Engine option: where centring / normalisation / transposition run (bit-identical either way)."
 
     @field_validator("min_sim", mode="after")
     @staticmethod
@@ -68,9 +70,28 @@ class ItemKNNScorer(Component, Trainable):
             return
         ds = _as_dataset(data)
         dev = _lib.require_device()
-        # host prep exactly as knn/item.py:141-157,202-228 (bitwise-identical f32 inputs)
-        ui, iu, means = knn_item_matrices(ds.interactions, self.config.explicit)
-        plan = engine.KnnBuildPlan.create(engine.DeviceCSR.from_host(ui, dev), engine.DeviceCSR.from_host(iu, dev))
+        it = ds.interactions
+        if self.config.prep == "device":
+            # knn/item.py:141-157,202-228 on the device (prep.cu): the COO triplets go up once, the f32
+            # inputs of the build are the same bits the SciPy path produces (tests/test_prep_gpu.py)
+            from . import prep
+
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+            d_ui, d_iu, d_means = prep.knn_item_matrices_device(
+                up(it.users), up(it.items), up(it.ratings) if self.config.explicit else None,
+                it.n_users, it.n_items, self.config.explicit,
+            )  # fmt: skip
+            means = None if d_means is None else d_means.cpu().numpy()
+            if means is not None and bool(torch.all(d_ui.values == 0)):
+                import warnings
+
+                warnings.warn("Ratings seem to have the same value, centering is not recommended.", UserWarning)
+        else:
+            # host prep with the reference's own SciPy calls
+            ui, iu, means = knn_item_matrices(it, self.config.explicit)
+            d_ui, d_iu = engine.DeviceCSR.from_host(ui, dev), engine.DeviceCSR.from_host(iu, dev)
+        self.prep_where = "device (prep.cu)" if self.config.prep == "device" else "host (SciPy)"
+        plan = engine.KnnBuildPlan.create(d_ui, d_iu)
         if self.config.save_nbrs:
             cols, vals, cnt = plan.build_topk(self.config.min_sim, int(self.config.save_nbrs))
             indptr, c, v = engine.topk_rows_to_csr(cols, vals, cnt)

@@ -44,6 +44,16 @@ def row_bounds_by_nnz(indptr: np.ndarray, world: int) -> np.ndarray:
     return np.maximum.accumulate(b)
 
 
+def shard_device_csr(m: engine.DeviceCSR, lo: int, hi: int) -> engine.DeviceCSR:
+    """Rows [lo, hi) of a device CSR as a device CSR of their own (offsets rebased)."""
+    a, b = int(m.h_indptr[lo]), int(m.h_indptr[hi])
+    hp = np.ascontiguousarray(m.h_indptr[lo : hi + 1] - m.h_indptr[lo]).astype(np.int32)
+    return engine.DeviceCSR(
+        (m.indptr[lo : hi + 1] - a).contiguous(), m.indices[a:b].contiguous(), m.values[a:b].contiguous(),
+        (hi - lo, m.shape[1]), hp,
+    )  # fmt: skip
+
+
 def shard_csr(csr: InteractionCSR, lo: int, hi: int) -> InteractionCSR:
     a, b = int(csr.indptr[lo]), int(csr.indptr[hi])
     return InteractionCSR(
@@ -113,19 +123,8 @@ class ShardedImplicitMFTrainer(ImplicitMFTrainer):
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         super().__init__(scorer, data, options)
-        k = self.config.embedding_size
-        dev = self.device
-        self.u_bounds = row_bounds_by_nnz(self.ui_host.indptr, self.world)
-        self.i_bounds = row_bounds_by_nnz(self.iu_host.indptr, self.world)
-        ulo, uhi = int(self.u_bounds[self.rank]), int(self.u_bounds[self.rank + 1])
-        ilo, ihi = int(self.i_bounds[self.rank]), int(self.i_bounds[self.rank + 1])
-        # replace the full matrices by this rank's row shards
-        self.ui = engine.DeviceCSR.from_host(shard_csr(self.ui_host, ulo, uhi), dev)
-        self.iu = engine.DeviceCSR.from_host(shard_csr(self.iu_host, ilo, ihi), dev)
-        self.u_plan = engine.ALSHalfPlan.create(self.ui, k)
-        self.i_plan = engine.ALSHalfPlan.create(self.iu, k)
-        self.u_slice = (ulo, uhi)
-        self.i_slice = (ilo, ihi)
+        ulo, uhi = self.u_slice
+        ilo, ihi = self.i_slice
         # every rank must start from the same factors (rank 0's draw)
         dist.broadcast(self.d_users, 0, group=group)
         dist.broadcast(self.d_items, 0, group=group)
@@ -135,6 +134,19 @@ class ShardedImplicitMFTrainer(ImplicitMFTrainer):
             self._try_peer_tables()
         self._graph = None
         torch.cuda.empty_cache()
+
+    def _make_plans(self, k: int) -> None:
+        """Plans for this rank's row shards only (contiguous ranges balanced by nonzeros); the full
+        matrices are replaced by the shards before any plan or workspace is sized."""
+        self.u_bounds = row_bounds_by_nnz(self.ui.h_indptr, self.world)
+        self.i_bounds = row_bounds_by_nnz(self.iu.h_indptr, self.world)
+        ulo, uhi = int(self.u_bounds[self.rank]), int(self.u_bounds[self.rank + 1])
+        ilo, ihi = int(self.i_bounds[self.rank]), int(self.i_bounds[self.rank + 1])
+        self.ui = shard_device_csr(self.ui, ulo, uhi)
+        self.iu = shard_device_csr(self.iu, ilo, ihi)
+        self.u_slice = (ulo, uhi)
+        self.i_slice = (ilo, ihi)
+        super()._make_plans(k)
 
     def _try_peer_tables(self) -> None:
         """
@@ -300,21 +312,38 @@ class ShardedImplicitMFTrainer(ImplicitMFTrainer):
 def sharded_knn_build_topk(
     plan: engine.KnnBuildPlan, min_sim: float, save_nbrs: int, group=None
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Item-sharded truncated build; every rank returns the full fixed-width result."""
+    """
+    Item-sharded truncated build; every rank returns the full fixed-width result.  Items are dealt to
+    the ranks in descending cost, snake order (``deal_by_cost`` on the device, no host sync); each
+    rank builds the rows it owns (its hot items cut into column pieces sized for ``plan.world`` GPUs);
+    ONE all-gather of the owned rows, packed as [cols | value bits | count], completes the result.
+    """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    # deal_by_cost on the device (no host sync): plan.order is already most-expensive-first
-    pos = torch.arange(plan.order.numel(), device=plan.order.device)
+    dev = plan.order.device
+    n_items = plan.order.numel()
+    pos = torch.arange(n_items, device=dev)
     lap, off = pos // world, pos % world
     owner = torch.where(lap % 2 == 0, off, world - 1 - off)
     order = plan.order[owner == rank].contiguous()
     cols, vals, cnt = plan.build_topk(min_sim, save_nbrs, order)
-    # rows are disjoint across ranks: zero the padding, then a sum is a gather
     K = cols.shape[1]
-    mask = torch.arange(K, device=cols.device)[None, :] < cnt[:, None]
-    cols = torch.where(mask, cols, torch.zeros_like(cols))
-    vals = torch.where(mask, vals, torch.zeros_like(vals))
-    for t in (cols, vals, cnt):
-        dist.all_reduce(t, group=group)
+    # every rank owns ceil or floor(n_items / world) rows: pad the packed block to the ceiling
+    m = -(-n_items // world)
+    send = torch.zeros((m, 2 * K + 1), dtype=torch.int32, device=dev)
+    o = order.long()
+    send[: o.numel(), :K] = cols[o]
+    send[: o.numel(), K : 2 * K] = vals[o].view(torch.int32)
+    send[: o.numel(), 2 * K] = cnt[o]
+    recv = torch.empty((world, m, 2 * K + 1), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(recv.view(world * m, 2 * K + 1), send, group=group)
+    for r in range(world):
+        if r == rank:
+            continue
+        rows = plan.order[owner == r].long()
+        blk = recv[r, : rows.numel()]
+        cols[rows] = blk[:, :K]
+        vals[rows] = blk[:, K : 2 * K].view(torch.float32)
+        cnt[rows] = blk[:, 2 * K]
     return cols, vals, cnt
 
 

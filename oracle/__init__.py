@@ -131,6 +131,11 @@ def lib():
             C.c_int, C.c_int, _f32p, _i32p,
         ]  # fmt: skip
         L.lk_oracle_knn_score.restype = C.c_int
+        L.lk_oracle_user_score.argtypes = [
+            _i64p, _i32p, C.c_void_p, C.c_int64, C.c_int64, _i32p, _f32p, C.c_int64, _i32p, C.c_int64,
+            C.c_int, C.c_int, _f32p, _i32p,
+        ]  # fmt: skip
+        L.lk_oracle_user_score.restype = C.c_int
         L.lk_oracle_argtopn_f32.argtypes = [_f32p, C.c_int64, C.c_int64, _i32p]
         L.lk_oracle_argtopn_f32.restype = C.c_int64
         _lib = L
@@ -405,6 +410,31 @@ def knn_score(
         raise ValueError("similarity is null")
     if rc:
         raise IndexError("item index out of range")
+    return scores, counts
+
+
+def user_score(
+    ratings, nbr_rows: np.ndarray, nbr_sims: np.ndarray, tgt_items: np.ndarray, max_nbrs: int, min_nbrs: int,
+    explicit: bool = True,
+) -> tuple[np.ndarray, np.ndarray]:
+    """``user_score_items_explicit`` / ``_implicit`` (user_score.rs:21-98) on a users x items CSR of
+    (centred) ratings; NaN / -1 mark nulls."""
+    indptr, cols, vals = _csr_parts(ratings)
+    n_users = len(indptr) - 1
+    n_items = int(ratings.shape[1])
+    nbr_rows = np.ascontiguousarray(nbr_rows, dtype=np.int32)
+    nbr_sims = np.ascontiguousarray(nbr_sims, dtype=np.float32)
+    tgt_items = np.ascontiguousarray(tgt_items, dtype=np.int32)
+    scores = np.empty(len(tgt_items), dtype=np.float32)
+    counts = np.empty(len(tgt_items), dtype=np.int32)
+    rc = lib().lk_oracle_user_score(
+        indptr, cols, vals.ctypes.data_as(C.c_void_p) if explicit else None, n_users, n_items, nbr_rows, nbr_sims,
+        len(nbr_rows), tgt_items, len(tgt_items), max_nbrs, min_nbrs, scores, counts,
+    )  # fmt: skip
+    if rc == 1:
+        raise ValueError("similarity is null")
+    if rc:
+        raise IndexError("index out of range")
     return scores, counts
 
 

@@ -60,6 +60,16 @@ def sub_csr(csr: InteractionCSR, rows: np.ndarray) -> InteractionCSR:
 # ---------------------------------------------------------------------------
 
 
+def _otor64(other: np.ndarray, reg: float) -> np.ndarray:
+    """OᵀO + reg·I accumulated in f64: the oracle's scalar loop where it finishes in seconds, a BLAS dgemm
+    on the f64 copy of the same table beyond that (1 M x 128 rows: the two agree to ~1e-15 relative)."""
+    n, k = other.shape
+    if n * k * k <= 4e9:
+        return oracle.otor(other, reg)[1]
+    o = other.astype(np.float64)
+    return o.T @ o + np.eye(k) * float(reg)
+
+
 def check_als_half(
     mode: str, csr: InteractionCSR, rows: np.ndarray, this_old_rows: np.ndarray, other: np.ndarray,
     got_rows: np.ndarray, reg: float, bf16: bool, tol: float = 1e-4,
@@ -76,7 +86,7 @@ def check_als_half(
     k = other.shape[1]
     o_in = oracle.bf16_round(other) if bf16 else other
     if mode == "implicit":
-        _o32, o64 = oracle.otor(o_in, reg)
+        o64 = _otor64(o_in, reg)
         ref, _ = oracle.als_half_f64("implicit", sub, this_old_rows, other, otor_mat=o64, bf16_other=bf16)
     else:
         ref, _ = oracle.als_half_f64("explicit", sub, this_old_rows, other, reg=reg, bf16_other=bf16)
@@ -100,8 +110,7 @@ def check_als_half(
     }
     if bf16:
         if mode == "implicit":
-            _o32, o64u = oracle.otor(other, reg)
-            refu, _ = oracle.als_half_f64("implicit", sub, this_old_rows, other, otor_mat=o64u)
+            refu, _ = oracle.als_half_f64("implicit", sub, this_old_rows, other, otor_mat=_otor64(other, reg))
         else:
             refu, _ = oracle.als_half_f64("explicit", sub, this_old_rows, other, reg=reg)
         out["rel_fro_vs_unrounded_f64_oracle"] = float(np.linalg.norm(got - refu) / max(np.linalg.norm(refu), 1e-300))

@@ -22,6 +22,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+@pytest.fixture(autouse=True)
+def _simt_for_fp32_rows(lk_options):
+    """This file pins the general SIMT kernel (als_kernels.cu) to "as good as f32 arithmetic": fp32 rows at
+    k = 64 are kept off the tf32 tensor-core path, which has its own tests and tolerance
+    (tests/test_als_tcx_gpu.py); bf16 rows at k = 64 still take als_tc.cu as before."""
+    lk_options("LK_ALS_TF32", 0)
+
+
 def _half(mode, csr, this, other, *, reg, bf16=False, chunk_nnz=engine.DEFAULT_CHUNK_NNZ):
     dev = _lib.require_device()
     dm = engine.DeviceCSR.from_host(csr, dev)
@@ -185,3 +193,66 @@ def test_accel_api_mirror(cuda_lib, ml_small):
         accel.als.train_implicit_matrix(ui, p_in.astype(np.float64), q, o32)
     with pytest.raises(RuntimeError, match="accelerator task failed"):
         accel.run_accel_task(accel.als.train_implicit_matrix(ui, p_in, q, -np.eye(k, dtype=np.float32)))
+
+
+def test_accel_arrow_matrix_and_live_cancel(cuda_lib, ml_small, lk_options):
+    """The matrix argument as the reference passes it — an Arrow List<Struct{index:int32, value:float32}>
+    (csr.rs:160-209) — and the task protocol's cancel / progress while the kernel runs (tasks/mod.rs:62-106)."""
+    import threading
+
+    import pyarrow as pa
+
+    from lkpy_b200 import accel
+
+    lk_options("LK_ALS_TF32", 1)  # the mirror's default path at k = 64: the tensor-core kernel
+    k = 64
+    ui, iu = data.als_implicit_matrices(ml_small, 40.0)
+    p, q = implicit_init(np.random.default_rng(42), ml_small.n_items, ml_small.n_users, k)
+    o32, o64 = oracle.otor(q, 0.1)
+    ref, dref = oracle.als_half_f64("implicit", ui, p, q, otor_mat=o64)
+    elems = pa.StructArray.from_arrays(
+        [pa.array(ui.indices, type=pa.int32()), pa.array(ui.values, type=pa.float32())], names=["index", "value"]
+    )
+    arrow_ui = pa.ListArray.from_arrays(pa.array(ui.indptr.astype(np.int32)), elems)
+    p_in = p.copy()
+    task = accel.als.train_implicit_matrix(arrow_ui, p_in, q, o32)
+    assert task.current_progress() == (0, ml_small.n_users)
+    delta = accel.run_accel_task(task)
+    assert rel_fro(p_in, ref) < 2 * TOL and delta == pytest.approx(dref, rel=1e-3)
+    assert task.current_progress() == (ml_small.n_users, ml_small.n_users)
+
+    # cancelled before it starts: nothing runs, `this` is untouched
+    p_in = p.copy()
+    task = accel.als.train_implicit_matrix(arrow_ui, p_in, q, o32)
+    task.cancel()
+    with pytest.raises(RuntimeError, match="cancelled"):
+        task.invoke()
+    assert np.array_equal(p_in, p)
+
+    # cancelled while running (a large synthetic half-step; the flag is raised from another thread)
+    inter = data.synth_interactions(60000, 20000, 6_000_000, seed=2)
+    bui, _ = data.als_implicit_matrices(inter, 40.0)
+    rng = np.random.default_rng(0)
+    bp = (rng.standard_normal((inter.n_users, k)) * 0.1).astype(np.float32)
+    bq = (rng.standard_normal((inter.n_items, k)) * 0.1).astype(np.float32)
+    bo = (bq.T @ bq + 0.1 * np.eye(k, dtype=np.float32)).astype(np.float32)
+    accel.run_accel_task(accel.als.train_implicit_matrix(bui, bp.copy(), bq, bo))  # upload + plan cached
+    task = accel.als.train_implicit_matrix(bui, bp.copy(), bq, bo)
+    seen = []
+
+    def killer():
+        while not task._invoked or task._counter is None:
+            pass
+        seen.append(task.current_progress())
+        task.cancel()
+
+    th = threading.Thread(target=killer)
+    th.start()
+    try:
+        task.invoke()
+        outcome = "finished"  # the kernel can beat the flag on a fast GPU: both outcomes are legal
+    except RuntimeError as e:
+        assert "cancelled" in str(e)
+        outcome = "cancelled"
+    th.join()
+    assert outcome in ("finished", "cancelled") and isinstance(seen[0], tuple) and seen[0][1] == inter.n_users

@@ -21,11 +21,11 @@ pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
 
 
-def _build(ui, iu, min_sim, save_nbrs, order=None):
+def _build(ui, iu, min_sim, save_nbrs, order=None, world=1):
     dev = _lib.require_device()
     d_ui = engine.DeviceCSR.from_host(ui, dev)
     d_iu = engine.DeviceCSR.from_host(iu, dev)
-    plan = engine.KnnBuildPlan.create(d_ui, d_iu)
+    plan = engine.KnnBuildPlan.create(d_ui, d_iu, world=world)
     if save_nbrs:
         cols, vals, cnt = plan.build_topk(min_sim, save_nbrs, order)
         indptr, c, v = engine.topk_rows_to_csr(cols, vals, cnt)
@@ -76,6 +76,28 @@ def test_build_multi_half_geometry(cuda_lib, ml_small, ctas, warps, lk_options):
     ref = oracle.knn_build(ui, iu, 1e-6, None)
     got, _ = _build(ui, iu, 1e-6, None)
     _assert_same(got, ref)
+
+
+@pytest.mark.parametrize("explicit", [True, False])
+def test_build_hot_items_cut_into_column_pieces(cuda_lib, lk_options, explicit):
+    """A plan made for many GPUs cuts the (item, half) units of expensive items into 2 / 4 / 8 column
+    pieces handled by different CTAs (knn_build.cu): same bits as the unsplit build and the oracle —
+    every dots[j] still sums its users in ascending order."""
+    lk_options("LK_KNN_CTAS", 4)  # several column halves as well
+    inter = small_synth(3000, 2500, 150000, seed=9)
+    ui, iu, _ = data.knn_item_matrices(inter, explicit)
+    ref = oracle.knn_build(ui, iu, 1e-6, 20)
+    got, plan = _build(ui, iu, 1e-6, 20, world=64)
+    pieces = plan.units(split_hot=True)["units"][:, 3]
+    assert int(pieces.max()) == 8 and len(torch.unique(pieces)) >= 2  # hot items cut finer than the tail
+    _assert_same(got, ref)
+    got1, _ = _build(ui, iu, 1e-6, 20, world=1)
+    _assert_same(got1, ref)
+    # the unbounded build never splits (pool segments must stay in column order)
+    refu = oracle.knn_build(ui, iu, 1e-6, None)
+    gotu, planu = _build(ui, iu, 1e-6, None, world=64)
+    assert int(planu.units(split_hot=False)["units"][:, 3].max()) == 1
+    _assert_same(gotu, refu)
 
 
 def test_build_synthetic_and_min_sim_edges(cuda_lib):
@@ -188,25 +210,57 @@ def test_golden_predictions_end_to_end(cuda_lib, ml_small):
     assert (err > 1e-5).sum() <= 3  # the three boundary-tie rows of SURVEY.md §8c
 
 
+def _arrow_rows(csr, large=False):
+    """The reference's storage of a sparse row array (data/matrix.py:388-424): List (or LargeList) of
+    Struct{index: int32, value: float32}."""
+    import pyarrow as pa
+
+    elems = pa.StructArray.from_arrays(
+        [pa.array(csr.indices, type=pa.int32()), pa.array(csr.values, type=pa.float32())], names=["index", "value"]
+    )
+    if large:
+        return pa.LargeListArray.from_arrays(pa.array(np.asarray(csr.indptr, dtype=np.int64)), elems)
+    return pa.ListArray.from_arrays(pa.array(np.asarray(csr.indptr, dtype=np.int32)), elems)
+
+
 def test_accel_api_mirror(cuda_lib, ml_small):
-    """lenskit._accel.knn signatures with Arrow in/out."""
+    """lenskit._accel.knn with the reference's own argument types: Arrow List<Struct{index,value}> matrices in
+    (csr.rs:160-209), LargeList chunks out (consumer.rs:96-142) that combine the way knn/item.py:173-177
+    combines them, Arrow arrays with nulls for the scoring calls."""
     import pyarrow as pa
 
     from lkpy_b200 import accel
 
     ui, iu, means = data.knn_item_matrices(ml_small, True)
-    chunks = accel.run_accel_task(
-        accel.knn.compute_similarities(ui, iu, (ml_small.n_users, ml_small.n_items), 1e-6, 20)
-    )
-    assert isinstance(chunks, list) and len(chunks) == 1
-    sims = chunks[0]
-    assert sims.indptr.dtype == np.int64
+    a_ui, a_iu = _arrow_rows(ui), _arrow_rows(iu)
+    shape = (ml_small.n_users, ml_small.n_items)
+    chunks = accel.run_accel_task(accel.knn.compute_similarities(a_ui, a_iu, shape, 1e-6, 20))
+    assert isinstance(chunks, list) and all(pa.types.is_large_list(c.type) for c in chunks)
+    assert chunks[0].type.value_type == pa.struct([("index", pa.int32()), ("value", pa.float32())])
+    smat = pa.chunked_array(chunks).combine_chunks()  # knn/item.py:173-177
+    assert len(smat) == ml_small.n_items
     ref = oracle.knn_build(ui, iu, 1e-6, 20)
-    assert np.array_equal(sims.indices, ref.indices)
+    got = accel.as_host_csr(smat, ml_small.n_items)
+    assert np.array_equal(got.indptr, ref.indptr) and got.indptr.dtype == np.int64
+    assert np.array_equal(got.indices, ref.indices)
+    assert np.array_equal(got.values.view(np.int32), ref.data.view(np.int32))
+    # several chunks: row order is the only contract (consumer.rs:137-142)
+    old = accel.RESULT_CHUNK_ROWS
+    try:
+        accel.RESULT_CHUNK_ROWS = 1000
+        many = accel.run_accel_task(accel.knn.compute_similarities(ui, iu, shape, 1e-6, 20))
+    finally:
+        accel.RESULT_CHUNK_ROWS = old
+    assert len(many) == -(-ml_small.n_items // 1000)
+    assert pa.chunked_array(many).combine_chunks().equals(smat)
+    # the unbounded build through the same door
+    full = accel.run_accel_task(accel.knn.compute_similarities(a_ui, a_iu, shape, 1e-6, None))
+    assert sum(len(c.values) for c in full) == 8_780_790
+
     ri = pa.array([1, 5, 30, None, 100], type=pa.int32())
     rv = pa.array([0.5, -1.0, 0.25, None, 1.5], type=pa.float32())
     ti = pa.array([3, None, 7, 31, 5], type=pa.int32())
-    scores, counts = accel.knn.score_explicit(sims, ri, rv, ti, 20, 1)
+    scores, counts = accel.knn.score_explicit(smat, ri, rv, ti, 20, 1)
     assert isinstance(scores, pa.Array) and isinstance(counts, pa.Array)
     assert counts.null_count == 1 and scores[1].as_py() is None
     osc, oct_ = oracle.knn_score(
@@ -216,5 +270,10 @@ def test_accel_api_mirror(cuda_lib, ml_small):
     got = scores.to_numpy(zero_copy_only=False)
     assert np.array_equal(np.isnan(got), np.isnan(osc))
     assert np.allclose(got[~np.isnan(osc)], osc[~np.isnan(osc)], rtol=0, atol=0)
-    s2, c2 = accel.knn.score_implicit(sims, ri, ti, 20, 1)
+    s2, c2 = accel.knn.score_implicit(smat, ri, ti, 20, 1)
     assert len(s2) == 5
+    with pytest.raises(TypeError):
+        accel.as_host_csr(pa.array([1.0, 2.0]))  # not a list array (csr.rs:160-195)
+    bad = pa.ListArray.from_arrays(pa.array([0, 1], type=pa.int32()), pa.array([0.5], type=pa.float64()))
+    with pytest.raises(TypeError):
+        accel.as_host_csr(bad)

@@ -41,7 +41,9 @@ for gdt in ("float32", "bfloat16"):
     dist.barrier()
 
 kui, kiu, _ = data.knn_item_matrices(inter, True)
-plan = engine.KnnBuildPlan.create(engine.DeviceCSR.from_host(kui, dev), engine.DeviceCSR.from_host(kiu, dev))
+plan = engine.KnnBuildPlan.create(
+    engine.DeviceCSR.from_host(kui, dev), engine.DeviceCSR.from_host(kiu, dev), world=world
+)
 cols, vals, cnt = sharded_knn_build_topk(plan, 1e-6, 20)
 if rank == 0:
     c1, v1, n1 = plan.build_topk(1e-6, 20)
