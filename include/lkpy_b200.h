@@ -286,6 +286,15 @@ typedef struct lk_knn_score_args {
      * of columns, and a row index is valid in [0, n_matrix_rows). */
     int32_t user_mode;
     int32_t n_matrix_rows;       /* user mode: rows of the rating matrix (item mode: unused, = n_items) */
+    /* Dense mode — d_tgt_indptr == NULL and d_tgt_items == NULL: every query is scored against ALL
+     * items in index order; d_scores / d_counts / d_acc_ws / d_acc_tw are [n_queries * n_items] (the two
+     * scratch arrays are only touched at targets that receive contributions), the slot map and d_acc_cnt
+     * are not used, the contribution pool is required.  A CTA handles a query; a query that touches more
+     * distinct targets than the CTA's shared list holds (16384) is not scored: its index is appended to
+     * d_deferred [n_queries] (count in d_n_deferred [1], zeroed by the call) for the caller to re-submit
+     * with an explicit target list. */
+    int32_t *d_deferred;
+    int32_t *d_n_deferred;
 } lk_knn_score_args;
 
 /* largest number of warps the scoring grid runs (one slotmap row each) */

@@ -137,6 +137,8 @@ class LkKnnScoreArgs(C.Structure):
         ("d_pool_cursor", vp),
         ("user_mode", C.c_int32),
         ("n_matrix_rows", C.c_int32),
+        ("d_deferred", vp),
+        ("d_n_deferred", vp),
     ]
 
 

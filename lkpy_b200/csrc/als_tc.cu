@@ -257,18 +257,21 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                 cp_async_commit();
             };
 
-            int cpre[NSTAGE - 1];
-            float vpre[NSTAGE - 1];
+            // Column indices run NSTAGE stages ahead of the gathers that need them (a ring of one index per
+            // stage and lane): with a distance of one stage every gather issue waited out the DRAM latency
+            // of its own index load (~2.5 k cycles per 32-row stage measured), which bounded the phase.
+            int cq[NSTAGE];
+            float vq[NSTAGE];
 #pragma unroll
-            for (int j = 0; j < NSTAGE - 1; j++) fetch(j, cpre[j], vpre[j]);
+            for (int j = 0; j < NSTAGE - 1; j++) fetch(j, cq[j], vq[j]);
 #pragma unroll
             for (int j = 0; j < NSTAGE - 1; j++) {
-                issue(j, j, cpre[j]);
-                vst[j] = vpre[j];
+                issue(j, j, cq[j]);
+                vst[j] = vq[j];
             }
-            int cnext;
-            float vnext;
-            fetch(NSTAGE - 1, cnext, vnext);
+            fetch(NSTAGE - 1, cq[NSTAGE - 1], vq[NSTAGE - 1]);
+#pragma unroll
+            for (int j = 0; j < NSTAGE - 1; j++) fetch(NSTAGE + j, cq[j], vq[j]);
 
             for (int it0 = 0; it0 < n_it; it0 += NSTAGE) {
 #pragma unroll
@@ -282,9 +285,9 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                             // the MMAs of iteration it-1 were the last commit on this buffer
                             mbar_wait(&stage_free[sj], ((free_par >> sj) & 1u) ^ 1u);
                         }
-                        issue(j, sj, cnext);
-                        if (j < n_it) vst[sj] = vnext;
-                        fetch(j + 1, cnext, vnext);
+                        issue(j, sj, cq[sj]);
+                        if (j < n_it) vst[sj] = vq[sj];
+                        fetch(j + NSTAGE, cq[sj], vq[sj]);  // the slot is free again: index of stage j + NSTAGE
                         // 2. stage `it` has landed
                         cp_async_wait<NSTAGE - 1>();
                         fence_proxy_async();
@@ -490,6 +493,13 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             // ------------------------------------------------------------------
             if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);  // next group, read after the closing barrier
             if (solve_mask) {
+                // old values of the rows about to be written: fetched before the solve, not waited for after it
+                float xold[2] = {0.0f, 0.0f};
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const int c = 2 * p + hh;
+                    if ((solve_mask >> c) & 1u) xold[p] = a.d_this[(size_t)s_misc[8 + 8 * c + 5] * k + gi];
+                }
                 ctc::solve4<false, GJ>(tmem_base, yv, ws, solve_bar, solve_par, tid);
                 __syncthreads();  // pivot flags
                 float dpart[2] = {0.0f, 0.0f};
@@ -503,7 +513,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                         } else {
                             float *tr = a.d_this + (size_t)rowc * k;
                             const float xn = yv[p];
-                            const float d = xn - tr[gi];
+                            const float d = xn - xold[p];
                             dpart[p] = d * d;
                             tr[gi] = xn;
                             for (int rr = 0; rr < a.n_replicas; rr++)

@@ -188,25 +188,32 @@ __global__ void __launch_bounds__(tcx::NT, 3) als_tcx_kernel(lk_als_args a)
             const float *vals = a.d_vals + begin;
             float4 ysum = make_float4(0.f, 0.f, 0.f, 0.f);  // features 4*fq..4*fq+3 over this lane's rows
 
-            // stage `it`: this lane's four rows are it*8 + 4*rq + i
-            auto fetch = [&](int it, float4 (&x)[4], float (&v)[4]) {
+            // Two-level software pipeline.  Stage `it` = rows it*8 + 4*rq + i (i = 0..3) for this lane.
+            //   column indices / values: a ring of IDX_AHEAD stages, loaded that far ahead, so that
+            //   the row loads: issued two stages ahead, never wait for the DRAM latency of their own index
+            //   (with both in one step every stage paid that latency in line — the phase was bound by it).
+            constexpr int IDX_AHEAD = 4;
+            int ci[IDX_AHEAD][4];
+            float vi[IDX_AHEAD][4];
+            auto load_idx = [&](int it, int (&c)[4], float (&v)[4]) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int idx = it * STAGE_ROWS + 4 * rq + i;
-                    if (it < n_it && idx < len) {
-                        const int c = __ldg(cols + idx);
-                        v[i] = __ldg(vals + idx);
-                        x[i] = load_quad(other, c, fq);
-                    } else {
-                        v[i] = 0.0f;
-                        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    const bool in = it < n_it && idx < len;
+                    c[i] = in ? __ldg(cols + idx) : -1;
+                    v[i] = in ? __ldg(vals + idx) : 0.0f;
                 }
             };
-            float4 xa[4], xb[4];
-            float va[4], vb[4];
-            fetch(0, xa, va);
-            fetch(1, xb, vb);
+            auto load_rows = [&](const int (&c)[4], float4 (&x)[4]) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    x[i] = c[i] >= 0 ? load_quad(other, c[i], fq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            float4 xr[2][4];
+#pragma unroll
+            for (int u = 0; u < IDX_AHEAD; u++) load_idx(u, ci[u], vi[u]);
+            load_rows(ci[0], xr[0]);
+            load_rows(ci[1], xr[1]);
 
             auto consume = [&](int it, float4 (&x)[4], float (&v)[4]) {
                 const int s = it % NSTAGE;
@@ -257,12 +264,15 @@ __global__ void __launch_bounds__(tcx::NT, 3) als_tcx_kernel(lk_als_args a)
                 free_par ^= (1u << s);
                 __syncwarp();
             };
-            for (int it = 0; it < n_it; it += 2) {
-                consume(it, xa, va);
-                fetch(it + 2, xa, va);
-                if (it + 1 < n_it) {
-                    consume(it + 1, xb, vb);
-                    fetch(it + 3, xb, vb);
+            for (int it0 = 0; it0 < n_it; it0 += IDX_AHEAD) {
+#pragma unroll
+                for (int u = 0; u < IDX_AHEAD; u++) {
+                    const int it = it0 + u;
+                    if (it < n_it) {
+                        consume(it, xr[u & 1], vi[u]);
+                        load_rows(ci[(u + 2) % IDX_AHEAD], xr[u & 1]);  // rows of stage it + 2
+                        load_idx(it + IDX_AHEAD, ci[u], vi[u]);         // indices of stage it + IDX_AHEAD
+                    }
                 }
             }
             // right-hand side of the chunk: fold the two row quads, features 4*fq..4*fq+3 -> lanes 0..15

@@ -31,12 +31,8 @@
 // (a user split would change the rounding).
 //
 // Ordering inside a warp: the products of up to 32 users are flattened over the
-// lanes in (user, column) order, so two lanes that hit the same column belong to
-// different users and the lower lane is the earlier user.  The groups of lanes
-// whose columns agree in their low 8 bits are found with one warp ballot per bit
-// (__match_any_sync itself was measured slower than the loop it replaced); round r
-// applies the r-th member of every group, so a batch takes 1-3 shared-memory
-// read-modify-write rounds instead of one round per user (~8).
+// lanes in (user, column) order and applied one user per round (the lanes of one
+// user hit distinct columns).
 
 #include <algorithm>
 #include <cstdlib>
@@ -46,7 +42,6 @@
 namespace lk {
 
 constexpr uint32_t SENT = 0xffffffffu;  // "never touched" accumulator marker (a NaN no product yields)
-constexpr int KEY_BITS = 8;             // column bits compared when grouping the lanes of a batch
 constexpr int HIST_BINS = 2048;
 
 __device__ __forceinline__ bool is_cand(uint32_t bits, float min_sim)
@@ -218,7 +213,6 @@ __global__ void __launch_bounds__(W * 32, 1024 / (W * 32)) knn_build_kernel(lk_k
             uint32_t *my = acc + warp * TW;
             const int iu0 = a.d_iu_indptr[item];
             const int m = a.d_iu_indptr[item + 1] - iu0;
-            const unsigned lt_mask = (1u << lane) - 1u;
             for (int t0 = 0; t0 < m; t0 += 32) {
                 int len = 0, base = 0;
                 float r = 0.0f;
@@ -254,26 +248,22 @@ __global__ void __launch_bounds__(W * 32, 1024 / (W * 32)) knn_build_kernel(lk_k
                         // diagonal excluded by index (item_train.rs:120-122); columns of other pieces are not ours
                         valid = col != item && j >= jlo && j < jhi;
                     }
-                    // lanes are in (user, column) order: lanes that share a column are different users, the
-                    // lower lane the earlier one.  Lanes whose columns agree in their low KEY_BITS bits are found
-                    // with one ballot per bit (a superset of the true same-column groups: a false member only
-                    // costs a round, never the order); round rr applies the rr-th member of every group.
-                    unsigned peers = __ballot_sync(FULL, valid);
-#pragma unroll
-                    for (int b = 0; b < KEY_BITS; b++) {
-                        const bool bit = (j >> b) & 1;
-                        const unsigned mb = __ballot_sync(FULL, bit);
-                        peers &= bit ? mb : ~mb;
-                    }
-                    const int rank = __popc(peers & lt_mask);
-                    const int rounds = __reduce_max_sync(FULL, valid ? rank : 0);
-                    for (int rr = 0; rr <= rounds; rr++) {
-                        if (valid && rank == rr) {
+                    // users in ascending order, one user per round: the lanes of one user hit distinct columns.
+                    // (Grouping lanes by column instead — __match_any_sync, or one ballot per column bit — was
+                    // measured slower on ML-25M-shaped data: a popular column is present in most users'
+                    // segments, so the rounds per batch stay near the number of users; profiles/r02_experiments.md.)
+                    unsigned pend = __ballot_sync(FULL, valid);
+                    while (pend) {
+                        const int leader = __ffs(pend) - 1;
+                        const int qq = __shfl_sync(FULL, q, leader);
+                        const bool mine = valid && q == qq;
+                        if (mine) {
                             const uint32_t old = my[j];
                             const float b = old == SENT ? 0.0f : __uint_as_float(old);
                             my[j] = __float_as_uint(__fadd_rn(b, prod));
                         }
                         __syncwarp();
+                        pend &= ~__ballot_sync(FULL, mine);
                     }
                 }
             }

@@ -532,6 +532,181 @@ __global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense variant: every query is scored against ALL items (d_tgt_items == NULL; the batch runner's
+// "score every candidate" case, the one the build+score metric is quoted on).  The list kernel above
+// makes several passes over a query's whole target list — 59 k slots of which ~3 k ever receive a
+// contribution — and needs a per-warp slot map; here the target of a contribution IS its output
+// position, so a CTA per query
+//   1. streams the NaN / 0 fill of the query's output rows (the only O(n_items) work left, coalesced),
+//   2. counts contributions with atomics directly on the count row and collects the targets touched
+//      for the first time in a shared-memory list,
+//   3. lays the touched targets' lists out in the contribution pool (block scan over the list),
+//   4. fills them, and
+//   5. gives every touched target to one thread: sort by history position, replay through the
+//      accumulator (vector sums in push order / BinaryHeap movement past max_nbrs) — the same bits as
+//      the sequential walk.
+// A query that touches more than DENSE_ACTIVE_CAP distinct targets is appended to d_deferred and left
+// to the list kernel (caller re-submits it with an explicit target list).
+// ---------------------------------------------------------------------------------------------
+constexpr int DENSE_THREADS = 256;
+constexpr int DENSE_ACTIVE_CAP = 16384;
+
+__global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_score_args a)
+{
+    extern __shared__ int32_t s_active[];  // [DENSE_ACTIVE_CAP] (dynamic: 64 KB)
+    __shared__ int s_scan[DENSE_THREADS / 32];
+    __shared__ int s_q, s_nactive, s_over, s_running;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = DENSE_THREADS / 32;
+    const bool user_mode = a.user_mode != 0;
+    const int n_rows = user_mode ? a.n_matrix_rows : a.n_items;
+    const bool explicit_fb = user_mode ? a.d_sim_vals != nullptr : a.d_ref_vals != nullptr;
+    const float qnan = __int_as_float(0x7fc00000);
+    const int limit = a.max_nbrs;
+    const int64_t NI = a.n_items;
+    PoolEnt *pool = reinterpret_cast<PoolEnt *>(a.d_pool);
+    int32_t *acc_off = reinterpret_cast<int32_t *>(a.d_acc_ws);  // [n_queries * n_items] scratch, touched targets only
+    int32_t *acc_cur = reinterpret_cast<int32_t *>(a.d_acc_tw);
+
+    for (;;) {
+        if (tid == 0) {
+            s_q = atomicAdd(a.d_work_counter, 1);
+            s_nactive = 0;
+            s_over = 0;
+            s_running = 0;
+        }
+        __syncthreads();
+        const int q = s_q;
+        if (q >= a.n_queries) break;
+        const int64_t r0 = a.d_ref_indptr[q], r1 = a.d_ref_indptr[q + 1];
+        float *scores = a.d_scores + (int64_t)q * NI;
+        int32_t *counts = a.d_counts + (int64_t)q * NI;
+        int32_t *qoff = acc_off + (int64_t)q * NI, *qcur = acc_cur + (int64_t)q * NI;
+
+        // 1. fill: null score, zero neighbours
+        for (int64_t x = tid; x < NI; x += DENSE_THREADS) {
+            scores[x] = qnan;
+            counts[x] = 0;
+        }
+        __syncthreads();
+
+        // 2. count: one warp per history entry, lanes over its matrix row
+        for (int64_t p = r0 + warp; p < r1; p += NW) {
+            const int r = a.d_ref_items[p];
+            if (r < 0 || r >= n_rows) continue;
+            const float hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
+            const int64_t e1 = a.d_sim_indptr[r + 1];
+            for (int64_t e = a.d_sim_indptr[r] + lane; e < e1; e += 32) {
+                const int t = __ldg(a.d_sim_cols + e);
+                const float w = user_mode ? hv : __ldg(a.d_sim_vals + e);
+                if (w != w) atomicCAS(a.d_status, 0, 2);  // "similarity is null" (accum.rs:146-152)
+                if (atomicAdd(&counts[t], 1) == 0) {
+                    const int idx = atomicAdd(&s_nactive, 1);
+                    if (idx < DENSE_ACTIVE_CAP) s_active[idx] = t; else s_over = 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int n_active = s_nactive;
+        if (s_over) {  // too many distinct targets for the shared list: hand the query to the list kernel
+            if (tid == 0) a.d_deferred[atomicAdd(a.d_n_deferred, 1)] = q;
+            __syncthreads();
+            continue;
+        }
+
+        // 3. lay out the lists: block-wide exclusive scan of the touched targets' counts
+        for (int i0 = 0; i0 < n_active; i0 += DENSE_THREADS) {
+            const int i = i0 + tid;
+            const int t = i < n_active ? s_active[i] : 0;
+            const int c = i < n_active ? __ldcg(&counts[t]) : 0;
+            int incl = warp_incl_scan(c, lane);
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < warp; w++) woff += s_scan[w];
+            const int run = s_running;
+            if (i < n_active) {
+                qoff[t] = run + woff + incl - c;
+                qcur[t] = 0;
+            }
+            __syncthreads();
+            if (tid == DENSE_THREADS - 1) s_running = run + woff + incl;
+            __syncthreads();
+        }
+        const int total = s_running;
+        if (tid == 0) s_base = atomicAdd(a.d_pool_cursor, (unsigned long long)total);
+        __syncthreads();
+        const unsigned long long base = s_base;
+        const bool fits = base + (unsigned long long)total <= (unsigned long long)a.pool_entries;
+        if (!fits) {
+            if (tid == 0) atomicCAS(a.d_status, 0, 3);  // pool too small (caller sizing error)
+            __syncthreads();
+            continue;
+        }
+
+        // 4. fill the lists (arrival order; sorted per target below)
+        for (int64_t p = r0 + warp; p < r1; p += NW) {
+            const int r = a.d_ref_items[p];
+            if (r < 0 || r >= n_rows) continue;
+            const float hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
+            const int64_t e1 = a.d_sim_indptr[r + 1];
+            for (int64_t e = a.d_sim_indptr[r] + lane; e < e1; e += 32) {
+                const int t = __ldg(a.d_sim_cols + e);
+                const float mv = a.d_sim_vals ? __ldg(a.d_sim_vals + e) : 0.0f;
+                const int kpos = atomicAdd(&qcur[t], 1);
+                PoolEnt ent;
+                ent.pos = (int32_t)(p - r0);
+                ent.sim = user_mode ? hv : mv;
+                ent.rv = user_mode ? mv : hv;
+                ent.pad = 0;
+                pool[base + (unsigned long long)(__ldcg(&qoff[t]) + kpos)] = ent;
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+
+        // 5. one thread per touched target: history order, then the accumulator
+        for (int i = tid; i < n_active; i += DENSE_THREADS) {
+            const int t = s_active[i];
+            const int n = __ldcg(&counts[t]);
+            PoolEnt *L = pool + base + (unsigned long long)__ldcg(&qoff[t]);
+            for (int u = 1; u < n; u++) {  // insertion sort by history position
+                const PoolEnt key = L[u];
+                int j = u - 1;
+                while (j >= 0 && L[j].pos > key.pos) {
+                    L[j + 1] = L[j];
+                    j--;
+                }
+                L[j + 1] = key;
+            }
+            float ws = 0.0f, tw = 0.0f;
+            int c = n;
+            if (n <= limit) {  // vector state: sums in push order (accum.rs:86-98, 196-231)
+                for (int u = 0; u < n; u++) tw = __fadd_rn(tw, L[u].sim);
+                if (explicit_fb)
+                    for (int u = 0; u < n; u++) ws = __fadd_rn(ws, __fmul_rn(L[u].sim, L[u].rv));
+            } else {
+                AccEnt d[SCORE_MAX_NBRS + 1];
+                int len = 0, is_heap = 0;
+                for (int u = 0; u < n; u++) {
+                    AccEnt ent;
+                    ent.w = L[u].sim;
+                    ent.v = L[u].rv;
+                    acc_push(d, len, is_heap, ent, limit);
+                }
+                for (int u = 0; u < len; u++) tw = __fadd_rn(tw, d[u].w);
+                for (int u = 0; u < len; u++) ws = __fadd_rn(ws, __fmul_rn(d[u].w, d[u].v));
+                c = len;
+            }
+            counts[t] = c;
+            if (c >= a.min_nbrs) scores[t] = explicit_fb ? ws / tw : tw;
+        }
+        __syncthreads();
+    }
+}
+
 constexpr int SCORE_WARPS_PER_SM = 16;
 
 }  // namespace lk
@@ -549,16 +724,32 @@ int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
     LK_REQUIRE(a.n_items >= 1 && a.n_queries >= 0, LK_ERR_INVALID, "bad shape");
     LK_REQUIRE(a.max_nbrs >= 1 && a.max_nbrs <= SCORE_MAX_NBRS, LK_ERR_UNSUPPORTED,
                "max_nbrs must be in 1..%d", SCORE_MAX_NBRS);
-    LK_REQUIRE(a.d_sim_indptr && a.d_sim_cols && a.d_ref_indptr && a.d_ref_items &&
-                   a.d_tgt_indptr && a.d_tgt_items && a.d_slotmap && a.d_acc_ws && a.d_acc_tw &&
-                   a.d_acc_cnt && a.d_scores && a.d_counts && a.d_work_counter && a.d_status,
+    const bool dense = a.d_tgt_items == nullptr && a.d_tgt_indptr == nullptr;  // every query against all items
+    LK_REQUIRE(a.d_sim_indptr && a.d_sim_cols && a.d_ref_indptr && a.d_ref_items && a.d_acc_ws && a.d_acc_tw &&
+                   a.d_scores && a.d_counts && a.d_work_counter && a.d_status,
                LK_ERR_INVALID, "lk_knn_score_batch: null pointer");
+    LK_REQUIRE(dense || (a.d_tgt_indptr && a.d_tgt_items && a.d_slotmap && a.d_acc_cnt), LK_ERR_INVALID,
+               "lk_knn_score_batch: null pointer (target lists)");
+    LK_REQUIRE(!dense || (a.d_pool && a.d_pool_cursor && a.d_deferred && a.d_n_deferred), LK_ERR_INVALID,
+               "lk_knn_score_batch: the dense (all-items) mode needs the contribution pool and the deferred list");
     LK_REQUIRE(a.user_mode ? a.d_ref_vals != nullptr : a.d_sim_vals != nullptr, LK_ERR_INVALID,
                "lk_knn_score_batch: the weights (similarities) are missing");
-    LK_REQUIRE(a.slotmap_warps >= 1, LK_ERR_INVALID, "slotmap too small");
+    LK_REQUIRE(dense || a.slotmap_warps >= 1, LK_ERR_INVALID, "slotmap too small");
     if (a.n_queries == 0) return LK_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LK_CUDA_TRY(cudaMemsetAsync(a.d_work_counter, 0, sizeof(int32_t), st));
+    if (dense) {
+        LK_REQUIRE(reinterpret_cast<uintptr_t>(a.d_pool) % 16 == 0 && a.pool_entries >= 0, LK_ERR_INVALID,
+                   "lk_knn_score_batch: bad contribution pool");
+        LK_CUDA_TRY(cudaMemsetAsync(a.d_pool_cursor, 0, sizeof(unsigned long long), st));
+        LK_CUDA_TRY(cudaMemsetAsync(a.d_n_deferred, 0, sizeof(int32_t), st));
+        const int grid = (int)std::min<int64_t>(a.n_queries, (int64_t)sm_count() * 3);
+        const int smem = DENSE_ACTIVE_CAP * (int)sizeof(int32_t);
+        LK_CUDA_TRY(cudaFuncSetAttribute(knn_score_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        knn_score_dense_kernel<<<grid, DENSE_THREADS, smem, st>>>(a);
+        LK_CUDA_TRY(cudaGetLastError());
+        return LK_OK;
+    }
     // as many warps as there are slot-map rows (the caller sizes them to the batch), at most the full grid
     const int64_t warps = std::min<int64_t>(a.slotmap_warps, lk_knn_score_warps());
     const int blocks = (int)((warps + 7) / 8);

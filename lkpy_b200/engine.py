@@ -527,6 +527,84 @@ class KnnScorerState:
         with self.lock:  # status word, work counter, pool and slot maps are shared by the callers of one state
             return self._score_locked(ref_indptr, ref_items, ref_vals, tgt_indptr, tgt_items, max_nbrs, min_nbrs)
 
+    def _pool_for(self, ref_items: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """Contribution pool: one 16-byte entry per (history entry, matrix-row entry) pair of the batch."""
+        dev = self.sim_cols.device
+        n_rows = self.n_rows if self.user_mode else self.n_items
+        r = ref_items.long()
+        ok = (r >= 0) & (r < n_rows)
+        rr = r.clamp(0, n_rows - 1)
+        total = int(((self.sim_indptr[rr + 1] - self.sim_indptr[rr]) * ok).sum().item())
+        pool = self.heap_scratch.get("pool")
+        if pool is None or pool.numel() < 4 * max(total, 1):
+            pool = torch.empty(4 * max(total, 1), dtype=torch.int32, device=dev)
+            self.heap_scratch["pool"] = pool
+            self.heap_scratch["pool_cursor"] = torch.zeros(1, dtype=torch.int64, device=dev)
+        return pool, self.heap_scratch["pool_cursor"]
+
+    def score_all_items(
+        self, ref_indptr: torch.Tensor, ref_items: torch.Tensor, ref_vals: torch.Tensor | None, max_nbrs: int, min_nbrs: int
+    ) -> tuple[torch.Tensor, torch.Tensor]:
+        """
+        Score every query against ALL items (the batch runner's case): returns (scores [n_queries, n_items]
+        with NaN nulls, counts [n_queries, n_items]).  Runs ``knn_score_dense_kernel`` — a CTA per query,
+        cost proportional to the contributions plus one streaming fill of the output — and re-submits the
+        rare query that touches more distinct targets than a CTA's shared list holds to the list kernel.
+        """
+        if not 1 <= int(max_nbrs) <= KNN_SCORE_MAX_NBRS:
+            raise ValueError(f"max_nbrs must be in 1..{KNN_SCORE_MAX_NBRS}")
+        with self.lock:
+            dev = self.sim_cols.device
+            nq, ni = ref_indptr.numel() - 1, self.n_items
+            scores = torch.empty((nq, ni), dtype=torch.float32, device=dev)
+            counts = torch.empty((nq, ni), dtype=torch.int32, device=dev)
+            ws = self.heap_scratch.get("dense_ws")
+            if ws is None or ws[0].numel() < nq * ni:
+                ws = (
+                    torch.empty(nq * ni, dtype=torch.int32, device=dev), torch.empty(nq * ni, dtype=torch.int32, device=dev),
+                    torch.empty(max(nq, 1), dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
+                )  # fmt: skip
+                self.heap_scratch["dense_ws"] = ws
+            off, cur, deferred, n_def = ws
+            if deferred.numel() < nq:
+                deferred = torch.empty(nq, dtype=torch.int32, device=dev)
+                self.heap_scratch["dense_ws"] = ws = (off, cur, deferred, n_def)
+            self.status.zero_()
+            pool, cursor = self._pool_for(ref_items)
+            a = LkKnnScoreArgs()
+            a.n_items = ni
+            a.d_sim_indptr, a.d_sim_cols, a.d_sim_vals = ptr(self.sim_indptr), ptr(self.sim_cols), ptr(self.sim_vals)
+            a.n_queries = nq
+            a.d_ref_indptr, a.d_ref_items, a.d_ref_vals = ptr(ref_indptr), ptr(ref_items), ptr(ref_vals)
+            a.max_nbrs, a.min_nbrs = int(max_nbrs), int(min_nbrs)
+            a.d_acc_ws, a.d_acc_tw = ptr(off), ptr(cur)
+            a.d_scores, a.d_counts = ptr(scores), ptr(counts)
+            a.d_work_counter, a.d_status = ptr(self.work_counter), ptr(self.status)
+            a.user_mode, a.n_matrix_rows = (1 if self.user_mode else 0), self.n_rows
+            a.d_pool, a.pool_entries, a.d_pool_cursor = ptr(pool), pool.numel() // 4, ptr(cursor)
+            a.d_deferred, a.d_n_deferred = ptr(deferred), ptr(n_def)
+            check(lib().lk_knn_score_batch(C.byref(a), stream_ptr()), "lk_knn_score_batch")
+            torch.cuda.current_stream().synchronize()
+            st = int(self.status.item())
+            if st == 2:
+                raise ValueError("similarity is null")
+            if st == 3:
+                raise _lib.EngineError("lk_knn_score_batch: contribution pool too small")
+            nd = int(n_def.item())
+            late = deferred[:nd].long().sort().values if nd else None
+        if late is not None:
+            # queries with more distinct targets than the dense kernel's shared list: the list kernel, explicit targets
+            lens = (ref_indptr[1:] - ref_indptr[:-1])[late]
+            sub_ptr = torch.zeros(nd + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(lens, 0, out=sub_ptr[1:])
+            idx = torch.cat([torch.arange(int(ref_indptr[q]), int(ref_indptr[q + 1]), device=dev) for q in late.tolist()])
+            tgt = torch.arange(ni, dtype=torch.int32, device=dev).repeat(nd)
+            tptr = torch.arange(nd + 1, dtype=torch.int64, device=dev) * ni
+            s2, c2 = self.score(sub_ptr, ref_items[idx], None if ref_vals is None else ref_vals[idx], tptr, tgt, max_nbrs, min_nbrs)
+            scores[late] = s2.view(nd, ni)
+            counts[late] = c2.view(nd, ni)
+        return scores, counts
+
     def _score_locked(self, ref_indptr, ref_items, ref_vals, tgt_indptr, tgt_items, max_nbrs, min_nbrs):
         dev = self.sim_cols.device
         nq = ref_indptr.numel() - 1
@@ -550,22 +628,13 @@ class KnnScorerState:
         a.d_scores, a.d_counts = ptr(scores), ptr(counts)
         a.d_work_counter, a.d_status = ptr(self.work_counter), ptr(self.status)
         a.user_mode, a.n_matrix_rows = (1 if self.user_mode else 0), self.n_rows
-        n_rows = self.n_rows if self.user_mode else self.n_items
         use_lists = self.USE_LISTS and ref_items.numel() > 0 and _lib.get_option("LK_KNN_SCORE_SEQ") != 1
         if use_lists:
             # contribution pool for the list-based kernel: one 16-byte entry per (reference item,
             # similarity-row entry) pair of the batch
-            r = ref_items.long()
-            ok = (r >= 0) & (r < n_rows)
-            rr = r.clamp(0, n_rows - 1)
-            total = int(((self.sim_indptr[rr + 1] - self.sim_indptr[rr]) * ok).sum().item())
-            pool = self.heap_scratch.get("pool")
-            if pool is None or pool.numel() < 4 * max(total, 1):
-                pool = torch.empty(4 * max(total, 1), dtype=torch.int32, device=dev)
-                self.heap_scratch["pool"] = pool
-                self.heap_scratch["pool_cursor"] = torch.zeros(1, dtype=torch.int64, device=dev)
+            pool, cursor = self._pool_for(ref_items)
             a.d_pool, a.pool_entries = ptr(pool), pool.numel() // 4
-            a.d_pool_cursor = ptr(self.heap_scratch["pool_cursor"])
+            a.d_pool_cursor = ptr(cursor)
         else:
             # the sequential kernel is the one that reads the per-warp heap states
             heap, per_warp = self._heap(max_nbrs, warps)

@@ -256,3 +256,34 @@ def test_accel_arrow_matrix_and_live_cancel(cuda_lib, ml_small, lk_options):
         outcome = "cancelled"
     th.join()
     assert outcome in ("finished", "cancelled") and isinstance(seen[0], tuple) and seen[0][1] == inter.n_users
+
+
+@pytest.mark.parametrize("tf32", [0, 1])
+def test_row_solves_match_reference_fold_in_vectors(cuda_lib, lk_options, tf32):
+    """tests/golden/als_ref_rows.npz holds outputs of the REFERENCE's own fold-in code
+    (_train_new_row als/_implicit.py:91-130, _train_bias_row_cholesky als/_explicit.py:121-147, run from the
+    reference source by make_golden.py): the device row solve reproduces them for k = 8 .. 128, on the SIMT
+    kernel and (k = 64) on the tensor-core kernel."""
+    lk_options("LK_ALS_TF32", tf32)
+    z = np.load(GOLD / "als_ref_rows.npz")
+    dev = _lib.require_device()
+    for c in range(int(z["n_cases"])):
+        g = lambda name: z[f"c{c}_{name}"]  # noqa: E731
+        k, other, items = int(g("k")), g("other"), g("items").astype(np.int32)
+        order = np.argsort(items, kind="stable")
+        for mode, vals, want in (("implicit", g("conf"), g("x_implicit")), ("explicit", g("rates"), g("x_explicit"))):
+            csr = data.InteractionCSR(
+                np.array([0, len(items)], dtype=np.int32), items[order], vals[order].astype(np.float32), (1, other.shape[0])
+            )
+            plan = engine.ALSHalfPlan.create(engine.DeviceCSR.from_host(csr, dev), k)
+            x = torch.zeros((1, k), device=dev)
+            d_other = torch.from_numpy(other).to(dev)
+            otor = torch.from_numpy(g("otor")).to(dev) if mode == "implicit" else None
+            engine.als_half_epoch(
+                plan, _lib.LK_ALS_IMPLICIT if mode == "implicit" else _lib.LK_ALS_EXPLICIT, x, d_other,
+                otor=otor, reg=float(g("reg")),
+            )  # fmt: skip
+            torch.cuda.synchronize()
+            assert int(plan.status.item()) == 0
+            got = x.cpu().numpy()[0]
+            assert rel_fro(got, want) < 1e-4, (c, mode, k, rel_fro(got, want))

@@ -185,6 +185,48 @@ def test_score_matches_oracle_exactly(cuda_lib, ml_small, explicit, max_nbrs, sa
         assert np.array_equal(g[ok].view(np.int32), osc[ok].view(np.int32))
 
 
+@pytest.mark.parametrize("explicit", [True, False])
+@pytest.mark.parametrize("max_nbrs,save_nbrs", [(20, 20), (5, None)])
+def test_score_all_items_dense_kernel(cuda_lib, ml_small, explicit, max_nbrs, save_nbrs, monkeypatch):
+    """Every query against all items (knn_score_dense_kernel): the same bits as the oracle's ScoreAccumulator,
+    heap ties included; with the unbounded model the heaviest users overflow the CTA's shared target list and
+    come back through the list kernel."""
+    ui, iu, means = data.knn_item_matrices(ml_small, explicit)
+    S = oracle.knn_build(ui, iu, 1e-6, save_nbrs)
+    R = ml_small.coo().tocsr()
+    rng = np.random.default_rng(23)
+    users = np.concatenate([[int(np.argmax(np.diff(R.indptr)))], rng.choice(ml_small.n_users, 30, replace=False)])
+    dev = _lib.require_device()
+    st = engine.KnnScorerState.create(S.shape[0], S.indptr, S.indices, S.data, dev)
+    hists = []
+    for u in users:
+        s, e = R.indptr[u], R.indptr[u + 1]
+        ri = R.indices[s:e].astype(np.int32)
+        perm = rng.permutation(len(ri))
+        ri = ri[perm].copy()
+        rv = R.data[s:e][perm].astype(np.float32)
+        if explicit:
+            rv = rv - means[ri]
+        if len(ri) > 4:
+            ri[1] = -1  # a null reference item
+        hists.append((ri, rv))
+    hists.append((np.zeros(0, np.int32), np.zeros(0, np.float32)))  # an empty history
+    ptr_ = np.cumsum([0] + [len(h[0]) for h in hists])
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    sc, ct = st.score_all_items(
+        t(ptr_), t(np.concatenate([h[0] for h in hists])),
+        t(np.concatenate([h[1] for h in hists])) if explicit else None, max_nbrs, 1,
+    )  # fmt: skip
+    sc, ct = sc.cpu().numpy(), ct.cpu().numpy()
+    all_items = np.arange(ml_small.n_items, dtype=np.int32)
+    for qi, (ri, rv) in enumerate(hists):
+        osc, oct_ = oracle.knn_score(S, ri, rv if explicit else None, all_items, max_nbrs, 1)
+        assert np.array_equal(ct[qi], oct_)
+        assert np.array_equal(np.isnan(sc[qi]), np.isnan(osc))
+        ok = ~np.isnan(osc)
+        assert np.array_equal(sc[qi][ok].view(np.int32), osc[ok].view(np.int32))
+
+
 def test_golden_predictions_end_to_end(cuda_lib, ml_small):
     """tests/models/item-item-preds.csv through GPU build + GPU scoring."""
     ui, iu, means = data.knn_item_matrices(ml_small, True)
