@@ -12,6 +12,8 @@ import numpy as np
 import pytest
 import torch
 
+from pathlib import Path
+
 import oracle
 from lkpy_b200 import _lib, data, engine
 
@@ -20,6 +22,7 @@ from helpers import explicit_init, implicit_init, rel_fro, small_synth
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
+GOLD = Path(__file__).resolve().parent / "golden"
 
 
 @pytest.fixture(autouse=True)
