@@ -676,6 +676,13 @@ def main() -> None:
                 "d2h_bytes_per_step": d2h, "api": api,
             }  # fmt: skip
             log(f"[bench] ALS {tag} e2e: {results[tag]['e2e']['value']:.3f} ms/epoch")
+            if world > 1:
+                from lkpy_b200.parallel import release_shared_pinned
+
+                barrier()
+                release_shared_pinned(hp)
+                release_shared_pinned(hq)
+            del hp, hq
             if tag == "bf16" and rank == 0 and world == 1 and not args.no_knn:
                 results["recommend"] = bench_recommend(args, tr, dev, peak, peak_src)
         if not args.no_parity:

@@ -115,6 +115,14 @@ def shared_pinned_tensor(name: str, shape: tuple[int, ...], dtype=torch.float32,
     return t
 
 
+def release_shared_pinned(t: torch.Tensor) -> None:
+    """Undo the page-locking of ``shared_pinned_tensor`` BEFORE the tensor is dropped: a mapping that is
+    unmapped while still registered leaves a stale registration behind, and a later host allocation that
+    lands on the same addresses makes its first copy fail with "invalid argument"."""
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+
+
 class ShardedImplicitMFTrainer(ImplicitMFTrainer):
     """Row-sharded implicit ALS over the ranks of the default process group."""
 
@@ -349,5 +357,5 @@ def sharded_knn_build_topk(
 
 __all__ = [
     "row_bounds_by_nnz", "shard_csr", "allgather_rows", "deal_by_cost", "ShardedImplicitMFTrainer",
-    "sharded_knn_build_topk", "ALSTrainerBase", "shared_pinned_tensor",
+    "sharded_knn_build_topk", "ALSTrainerBase", "shared_pinned_tensor", "release_shared_pinned",
 ]  # fmt: skip
