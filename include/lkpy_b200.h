@@ -288,17 +288,17 @@ typedef struct lk_knn_score_args {
     int32_t n_matrix_rows;       /* user mode: rows of the rating matrix (item mode: unused, = n_items) */
     /* Dense mode — d_tgt_indptr == NULL and d_tgt_items == NULL: every query is scored against ALL
      * items in index order; d_scores / d_counts / d_acc_ws / d_acc_tw are [n_queries * n_items] (the two
-     * scratch arrays are only touched at targets that receive contributions), the slot map and d_acc_cnt
-     * are not used, the contribution pool is required.  A CTA handles a query; a query that touches more
-     * distinct targets than the CTA's shared list holds (16384) is not scored: its index is appended to
-     * d_deferred [n_queries] (count in d_n_deferred [1], zeroed by the call) for the caller to re-submit
-     * with an explicit target list. */
-    int32_t *d_deferred;
-    int32_t *d_n_deferred;
+     * scratch arrays are only touched at targets that receive contributions), d_acc_cnt is not used, the
+     * contribution pool is required.  A CTA handles a query; d_slotmap provides one n_items row per CTA
+     * (slotmap_warps >= lk_knn_score_dense_ctas()) for the touched-target list of the heaviest queries. */
+    int32_t *d_deferred;         /* reserved (unused) */
+    int32_t *d_n_deferred;       /* reserved (unused) */
 } lk_knn_score_args;
 
 /* largest number of warps the scoring grid runs (one slotmap row each) */
 LK_API int64_t lk_knn_score_warps(void);
+/* number of CTAs of the dense (all-items) scoring grid: one n_items row of d_slotmap each */
+LK_API int64_t lk_knn_score_dense_ctas(void);
 LK_API int lk_knn_score_batch(const lk_knn_score_args *args, void *stream);
 
 /* ------------------------------------------------------------------------

@@ -16,7 +16,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "liblkpy_b200.so"
-SOURCES = ["capi.cu", "als_kernels.cu", "als_tc.cu", "als_tcx.cu", "knn_build.cu", "knn_score.cu", "topn.cu", "prep.cu"]
+SOURCES = ["capi.cu", "als_kernels.cu", "als_tc.cu", "als_tcx.cu", "als_tc128.cu", "knn_build.cu", "knn_score.cu", "topn.cu", "prep.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
@@ -37,6 +37,7 @@ def _stale() -> bool:
     t = LIB.stat().st_mtime
     deps = [CSRC / s for s in SOURCES] + [
         CSRC / "common.cuh", CSRC / "als_common.cuh", CSRC / "tc_common.cuh", CSRC / "chol_tc.cuh",
+        CSRC / "chol_tc128.cuh",
     ]  # fmt: skip
     deps.append(CSRC.parent.parent / "include" / "lkpy_b200.h")
     return any(d.stat().st_mtime > t for d in deps)

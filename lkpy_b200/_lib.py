@@ -165,6 +165,7 @@ SYMBOLS: dict[str, tuple] = {
     "lk_knn_pool_to_csr": (C.c_int, [C.POINTER(LkKnnBuildArgs), vp, vp, vp, vp]),
     "lk_knn_prep_columns": (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, vp, vp]),
     "lk_knn_score_warps": (C.c_int64, []),
+    "lk_knn_score_dense_ctas": (C.c_int64, []),
     "lk_knn_score_batch": (C.c_int, [C.POINTER(LkKnnScoreArgs), vp]),
     "lk_topn_max": (C.c_int, []),
     "lk_topn_columns": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, vp, vp, vp, vp]),

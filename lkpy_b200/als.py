@@ -324,9 +324,14 @@ class ALSTrainerBase(ModelTrainer):
     def solve_kernel_name(self) -> str:
         """Which row-solve kernel the configuration runs (bench.py's roofline label)."""
         k = self.config.embedding_size
-        tc = k == 64 and _lib.get_option("LK_ALS_TC") != 0
-        if tc and (self.bf16 or _lib.get_option("LK_ALS_TF32") != 0):
+        on = _lib.get_option("LK_ALS_TC") != 0
+        uniform = self.MODE != _lib.LK_ALS_IMPLICIT or not getattr(self.config, "use_ratings", False)
+        if on and k == 64 and self.bf16 and uniform:
             return "als_tc_kernel"
+        if on and k == 64 and _lib.get_option("LK_ALS_TF32") != 0:
+            return "als_tcx_kernel"
+        if on and k == 128 and self.bf16 and uniform:
+            return "als_tc128_kernel"
         return "als_half_kernel"
 
     def launches_per_epoch(self) -> int:

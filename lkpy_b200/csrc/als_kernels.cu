@@ -449,6 +449,7 @@ __global__ void otor_reduce_kernel(const float *__restrict__ partial, int nblock
 
 int launch_als_tc(const lk_als_args &a, cudaStream_t st);   // als_tc.cu  (bf16 rows, uniform weights)
 int launch_als_tcx(const lk_als_args &a, cudaStream_t st);  // als_tcx.cu (fp32 rows / non-uniform weights, tf32 x3)
+int launch_als_tc128(const lk_als_args &a, cudaStream_t st);  // als_tc128.cu (k = 128, bf16 rows, uniform weights)
 
 static int pad_features(int k) { return k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : -1; }
 
@@ -593,6 +594,8 @@ int lk_als_half_epoch(const lk_als_args *args, void *stream)
         int rc = launch_als_tc(a, st);
         if (rc <= 0) return rc;
         rc = launch_als_tcx(a, st);
+        if (rc <= 0) return rc;
+        rc = launch_als_tc128(a, st);
         if (rc <= 0) return rc;
     }
     if (a.other_dtype == LK_DTYPE_F32) return dispatch_k<float>(a, st);

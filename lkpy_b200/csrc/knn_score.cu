@@ -539,27 +539,50 @@ __global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args 
 // contribution — and needs a per-warp slot map; here the target of a contribution IS its output
 // position, so a CTA per query
 //   1. streams the NaN / 0 fill of the query's output rows (the only O(n_items) work left, coalesced),
-//   2. counts contributions with atomics directly on the count row and collects the targets touched
-//      for the first time in a shared-memory list,
+//   2. flattens the contributions of a chunk of the history over its 256 threads (row extents in shared
+//      memory, block scan, one binary search per contribution) and counts them with atomics directly on
+//      the count row, collecting the targets touched for the first time (shared list, spilling into a
+//      per-CTA global list for the heaviest users),
 //   3. lays the touched targets' lists out in the contribution pool (block scan over the list),
-//   4. fills them, and
+//   4. fills them with the same flattened walk, and
 //   5. gives every touched target to one thread: sort by history position, replay through the
 //      accumulator (vector sums in push order / BinaryHeap movement past max_nbrs) — the same bits as
 //      the sequential walk.
-// A query that touches more than DENSE_ACTIVE_CAP distinct targets is appended to d_deferred and left
-// to the list kernel (caller re-submits it with an explicit target list).
 // ---------------------------------------------------------------------------------------------
 constexpr int DENSE_THREADS = 256;
-constexpr int DENSE_ACTIVE_CAP = 16384;
+constexpr int DENSE_ACTIVE_CAP = 8192;  // touched targets kept in shared memory (the rest: d_slotmap row of the CTA)
+constexpr int DENSE_HIST_CHUNK = 2048;  // history entries flattened at a time
+
+struct DenseSmem {
+    int32_t active[DENSE_ACTIVE_CAP];
+    long long row0[DENSE_HIST_CHUNK];  // first matrix entry of the history entry's row
+    int32_t pre[DENSE_HIST_CHUNK + 1];  // exclusive prefix of the row lengths
+    float hv[DENSE_HIST_CHUNK];         // the history entry's value
+};
+
+__device__ __forceinline__ int block_excl_scan(int v, int *s_scan, int *s_carry, int tid, int lane, int warp)
+{
+    // exclusive scan of v over the block, continuing from *s_carry; returns this thread's offset and advances the carry
+    const int incl = warp_incl_scan(v, lane);
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_scan[w];
+    const int carry = *s_carry;
+    __syncthreads();
+    if (tid == DENSE_THREADS - 1) *s_carry = carry + woff + incl;
+    __syncthreads();
+    return carry + woff + incl - v;
+}
 
 __global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_score_args a)
 {
-    extern __shared__ int32_t s_active[];  // [DENSE_ACTIVE_CAP] (dynamic: 64 KB)
+    extern __shared__ __align__(16) unsigned char dense_raw[];
+    DenseSmem &sm = *reinterpret_cast<DenseSmem *>(dense_raw);
     __shared__ int s_scan[DENSE_THREADS / 32];
-    __shared__ int s_q, s_nactive, s_over, s_running;
+    __shared__ int s_q, s_nactive, s_carry;
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = DENSE_THREADS / 32;
     const bool user_mode = a.user_mode != 0;
     const int n_rows = user_mode ? a.n_matrix_rows : a.n_items;
     const bool explicit_fb = user_mode ? a.d_sim_vals != nullptr : a.d_ref_vals != nullptr;
@@ -569,13 +592,13 @@ __global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_s
     PoolEnt *pool = reinterpret_cast<PoolEnt *>(a.d_pool);
     int32_t *acc_off = reinterpret_cast<int32_t *>(a.d_acc_ws);  // [n_queries * n_items] scratch, touched targets only
     int32_t *acc_cur = reinterpret_cast<int32_t *>(a.d_acc_tw);
+    int32_t *g_active = a.d_slotmap + (size_t)blockIdx.x * NI;  // overflow of the shared list
+    auto active_at = [&](int i) { return i < DENSE_ACTIVE_CAP ? sm.active[i] : g_active[i - DENSE_ACTIVE_CAP]; };
 
     for (;;) {
         if (tid == 0) {
             s_q = atomicAdd(a.d_work_counter, 1);
             s_nactive = 0;
-            s_over = 0;
-            s_running = 0;
         }
         __syncthreads();
         const int q = s_q;
@@ -592,84 +615,99 @@ __global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_s
         }
         __syncthreads();
 
-        // 2. count: one warp per history entry, lanes over its matrix row
-        for (int64_t p = r0 + warp; p < r1; p += NW) {
-            const int r = a.d_ref_items[p];
-            if (r < 0 || r >= n_rows) continue;
-            const float hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
-            const int64_t e1 = a.d_sim_indptr[r + 1];
-            for (int64_t e = a.d_sim_indptr[r] + lane; e < e1; e += 32) {
-                const int t = __ldg(a.d_sim_cols + e);
-                const float w = user_mode ? hv : __ldg(a.d_sim_vals + e);
-                if (w != w) atomicCAS(a.d_status, 0, 2);  // "similarity is null" (accum.rs:146-152)
-                if (atomicAdd(&counts[t], 1) == 0) {
-                    const int idx = atomicAdd(&s_nactive, 1);
-                    if (idx < DENSE_ACTIVE_CAP) s_active[idx] = t; else s_over = 1;
+        // walk over the contributions of the query, flattened over the block: fn(history position, matrix entry, value)
+        auto for_each_contribution = [&](auto fn) {
+            for (int64_t h0 = r0; h0 < r1; h0 += DENSE_HIST_CHUNK) {
+                const int nh = (int)min((int64_t)DENSE_HIST_CHUNK, r1 - h0);
+                if (tid == 0) s_carry = 0;
+                __syncthreads();
+                for (int i0 = 0; i0 < nh; i0 += DENSE_THREADS) {
+                    const int i = i0 + tid;
+                    int len = 0;
+                    if (i < nh) {
+                        const int r = a.d_ref_items[h0 + i];
+                        long long e0 = 0;
+                        if (r >= 0 && r < n_rows) {  // null / unknown reference items contribute nothing
+                            e0 = a.d_sim_indptr[r];
+                            len = (int)(a.d_sim_indptr[r + 1] - e0);
+                        }
+                        sm.row0[i] = e0;
+                        sm.hv[i] = a.d_ref_vals ? a.d_ref_vals[h0 + i] : 0.0f;
+                    }
+                    const int off = block_excl_scan(len, s_scan, &s_carry, tid, lane, warp);
+                    if (i < nh) sm.pre[i] = off;
                 }
+                if (tid == 0) sm.pre[nh] = s_carry;
+                __syncthreads();
+                const int total = sm.pre[nh];
+                for (int c = tid; c < total; c += DENSE_THREADS) {
+                    int lo = 0, hi = nh;  // last i with pre[i] <= c
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sm.pre[mid] <= c) lo = mid; else hi = mid;
+                    }
+                    fn((int)(h0 - r0) + lo, sm.row0[lo] + (c - sm.pre[lo]), sm.hv[lo]);
+                }
+                __syncthreads();
             }
-        }
+        };
+
+        // 2. count
+        for_each_contribution([&](int, long long e, float hv) {
+            const int t = __ldg(a.d_sim_cols + e);
+            const float w = user_mode ? hv : __ldg(a.d_sim_vals + e);
+            if (w != w) atomicCAS(a.d_status, 0, 2);  // "similarity is null" (accum.rs:146-152)
+            if (atomicAdd(&counts[t], 1) == 0) {
+                const int idx = atomicAdd(&s_nactive, 1);
+                if (idx < DENSE_ACTIVE_CAP) sm.active[idx] = t; else g_active[idx - DENSE_ACTIVE_CAP] = t;
+            }
+        });
+        __threadfence_block();
         __syncthreads();
         const int n_active = s_nactive;
-        if (s_over) {  // too many distinct targets for the shared list: hand the query to the list kernel
-            if (tid == 0) a.d_deferred[atomicAdd(a.d_n_deferred, 1)] = q;
-            __syncthreads();
-            continue;
-        }
 
         // 3. lay out the lists: block-wide exclusive scan of the touched targets' counts
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
         for (int i0 = 0; i0 < n_active; i0 += DENSE_THREADS) {
             const int i = i0 + tid;
-            const int t = i < n_active ? s_active[i] : 0;
+            const int t = i < n_active ? active_at(i) : 0;
             const int c = i < n_active ? __ldcg(&counts[t]) : 0;
-            int incl = warp_incl_scan(c, lane);
-            if (lane == 31) s_scan[warp] = incl;
-            __syncthreads();
-            int woff = 0;
-            for (int w = 0; w < warp; w++) woff += s_scan[w];
-            const int run = s_running;
+            const int off = block_excl_scan(c, s_scan, &s_carry, tid, lane, warp);
             if (i < n_active) {
-                qoff[t] = run + woff + incl - c;
+                qoff[t] = off;
                 qcur[t] = 0;
             }
-            __syncthreads();
-            if (tid == DENSE_THREADS - 1) s_running = run + woff + incl;
-            __syncthreads();
         }
-        const int total = s_running;
+        const int total = s_carry;
         if (tid == 0) s_base = atomicAdd(a.d_pool_cursor, (unsigned long long)total);
+        __threadfence_block();
         __syncthreads();
         const unsigned long long base = s_base;
-        const bool fits = base + (unsigned long long)total <= (unsigned long long)a.pool_entries;
-        if (!fits) {
+        if (base + (unsigned long long)total > (unsigned long long)a.pool_entries) {
             if (tid == 0) atomicCAS(a.d_status, 0, 3);  // pool too small (caller sizing error)
             __syncthreads();
             continue;
         }
 
         // 4. fill the lists (arrival order; sorted per target below)
-        for (int64_t p = r0 + warp; p < r1; p += NW) {
-            const int r = a.d_ref_items[p];
-            if (r < 0 || r >= n_rows) continue;
-            const float hv = a.d_ref_vals ? a.d_ref_vals[p] : 0.0f;
-            const int64_t e1 = a.d_sim_indptr[r + 1];
-            for (int64_t e = a.d_sim_indptr[r] + lane; e < e1; e += 32) {
-                const int t = __ldg(a.d_sim_cols + e);
-                const float mv = a.d_sim_vals ? __ldg(a.d_sim_vals + e) : 0.0f;
-                const int kpos = atomicAdd(&qcur[t], 1);
-                PoolEnt ent;
-                ent.pos = (int32_t)(p - r0);
-                ent.sim = user_mode ? hv : mv;
-                ent.rv = user_mode ? mv : hv;
-                ent.pad = 0;
-                pool[base + (unsigned long long)(__ldcg(&qoff[t]) + kpos)] = ent;
-            }
-        }
+        for_each_contribution([&](int pos, long long e, float hv) {
+            const int t = __ldg(a.d_sim_cols + e);
+            const float mv = a.d_sim_vals ? __ldg(a.d_sim_vals + e) : 0.0f;
+            const int kpos = atomicAdd(&qcur[t], 1);
+            PoolEnt ent;
+            ent.pos = pos;
+            ent.sim = user_mode ? hv : mv;
+            ent.rv = user_mode ? mv : hv;
+            ent.pad = 0;
+            pool[base + (unsigned long long)(__ldcg(&qoff[t]) + kpos)] = ent;
+        });
         __threadfence_block();
         __syncthreads();
 
         // 5. one thread per touched target: history order, then the accumulator
         for (int i = tid; i < n_active; i += DENSE_THREADS) {
-            const int t = s_active[i];
+            const int t = active_at(i);
             const int n = __ldcg(&counts[t]);
             PoolEnt *L = pool + base + (unsigned long long)__ldcg(&qoff[t]);
             for (int u = 1; u < n; u++) {  // insertion sort by history position
@@ -717,6 +755,8 @@ extern "C" {
 
 int64_t lk_knn_score_warps(void) { return (int64_t)sm_count() * SCORE_WARPS_PER_SM; }
 
+int64_t lk_knn_score_dense_ctas(void) { return (int64_t)sm_count() * 3; }
+
 int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
 {
     LK_REQUIRE(args != nullptr, LK_ERR_INVALID, "lk_knn_score_batch: null args");
@@ -730,8 +770,10 @@ int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
                LK_ERR_INVALID, "lk_knn_score_batch: null pointer");
     LK_REQUIRE(dense || (a.d_tgt_indptr && a.d_tgt_items && a.d_slotmap && a.d_acc_cnt), LK_ERR_INVALID,
                "lk_knn_score_batch: null pointer (target lists)");
-    LK_REQUIRE(!dense || (a.d_pool && a.d_pool_cursor && a.d_deferred && a.d_n_deferred), LK_ERR_INVALID,
-               "lk_knn_score_batch: the dense (all-items) mode needs the contribution pool and the deferred list");
+    LK_REQUIRE(!dense || (a.d_pool && a.d_pool_cursor && a.d_slotmap && a.slotmap_warps >= lk_knn_score_dense_ctas()),
+               LK_ERR_INVALID,
+               "lk_knn_score_batch: the dense (all-items) mode needs the contribution pool and one n_items row of "
+               "d_slotmap per CTA (lk_knn_score_dense_ctas)");
     LK_REQUIRE(a.user_mode ? a.d_ref_vals != nullptr : a.d_sim_vals != nullptr, LK_ERR_INVALID,
                "lk_knn_score_batch: the weights (similarities) are missing");
     LK_REQUIRE(dense || a.slotmap_warps >= 1, LK_ERR_INVALID, "slotmap too small");
@@ -742,9 +784,8 @@ int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
         LK_REQUIRE(reinterpret_cast<uintptr_t>(a.d_pool) % 16 == 0 && a.pool_entries >= 0, LK_ERR_INVALID,
                    "lk_knn_score_batch: bad contribution pool");
         LK_CUDA_TRY(cudaMemsetAsync(a.d_pool_cursor, 0, sizeof(unsigned long long), st));
-        LK_CUDA_TRY(cudaMemsetAsync(a.d_n_deferred, 0, sizeof(int32_t), st));
-        const int grid = (int)std::min<int64_t>(a.n_queries, (int64_t)sm_count() * 3);
-        const int smem = DENSE_ACTIVE_CAP * (int)sizeof(int32_t);
+        const int grid = (int)std::min<int64_t>(a.n_queries, lk_knn_score_dense_ctas());
+        const int smem = (int)sizeof(DenseSmem);
         LK_CUDA_TRY(cudaFuncSetAttribute(knn_score_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         knn_score_dense_kernel<<<grid, DENSE_THREADS, smem, st>>>(a);
         LK_CUDA_TRY(cudaGetLastError());

@@ -548,8 +548,7 @@ class KnnScorerState:
         """
         Score every query against ALL items (the batch runner's case): returns (scores [n_queries, n_items]
         with NaN nulls, counts [n_queries, n_items]).  Runs ``knn_score_dense_kernel`` — a CTA per query,
-        cost proportional to the contributions plus one streaming fill of the output — and re-submits the
-        rare query that touches more distinct targets than a CTA's shared list holds to the list kernel.
+        cost proportional to the contributions plus one streaming fill of the output.
         """
         if not 1 <= int(max_nbrs) <= KNN_SCORE_MAX_NBRS:
             raise ValueError(f"max_nbrs must be in 1..{KNN_SCORE_MAX_NBRS}")
@@ -565,12 +564,13 @@ class KnnScorerState:
                     torch.empty(max(nq, 1), dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
                 )  # fmt: skip
                 self.heap_scratch["dense_ws"] = ws
-            off, cur, deferred, n_def = ws
-            if deferred.numel() < nq:
-                deferred = torch.empty(nq, dtype=torch.int32, device=dev)
-                self.heap_scratch["dense_ws"] = ws = (off, cur, deferred, n_def)
+            off, cur, _deferred, _n_def = ws
             self.status.zero_()
             pool, cursor = self._pool_for(ref_items)
+            ctas = int(lib().lk_knn_score_dense_ctas())
+            spill = self.heap_scratch.get("dense_spill")
+            if spill is None or spill.numel() < ctas * ni:
+                spill = self.heap_scratch["dense_spill"] = torch.empty(ctas * ni, dtype=torch.int32, device=dev)
             a = LkKnnScoreArgs()
             a.n_items = ni
             a.d_sim_indptr, a.d_sim_cols, a.d_sim_vals = ptr(self.sim_indptr), ptr(self.sim_cols), ptr(self.sim_vals)
@@ -582,7 +582,7 @@ class KnnScorerState:
             a.d_work_counter, a.d_status = ptr(self.work_counter), ptr(self.status)
             a.user_mode, a.n_matrix_rows = (1 if self.user_mode else 0), self.n_rows
             a.d_pool, a.pool_entries, a.d_pool_cursor = ptr(pool), pool.numel() // 4, ptr(cursor)
-            a.d_deferred, a.d_n_deferred = ptr(deferred), ptr(n_def)
+            a.d_slotmap, a.slotmap_warps = ptr(spill), ctas  # per-CTA overflow of the touched-target list
             check(lib().lk_knn_score_batch(C.byref(a), stream_ptr()), "lk_knn_score_batch")
             torch.cuda.current_stream().synchronize()
             st = int(self.status.item())
@@ -590,19 +590,6 @@ class KnnScorerState:
                 raise ValueError("similarity is null")
             if st == 3:
                 raise _lib.EngineError("lk_knn_score_batch: contribution pool too small")
-            nd = int(n_def.item())
-            late = deferred[:nd].long().sort().values if nd else None
-        if late is not None:
-            # queries with more distinct targets than the dense kernel's shared list: the list kernel, explicit targets
-            lens = (ref_indptr[1:] - ref_indptr[:-1])[late]
-            sub_ptr = torch.zeros(nd + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(lens, 0, out=sub_ptr[1:])
-            idx = torch.cat([torch.arange(int(ref_indptr[q]), int(ref_indptr[q + 1]), device=dev) for q in late.tolist()])
-            tgt = torch.arange(ni, dtype=torch.int32, device=dev).repeat(nd)
-            tptr = torch.arange(nd + 1, dtype=torch.int64, device=dev) * ni
-            s2, c2 = self.score(sub_ptr, ref_items[idx], None if ref_vals is None else ref_vals[idx], tptr, tgt, max_nbrs, min_nbrs)
-            scores[late] = s2.view(nd, ni)
-            counts[late] = c2.view(nd, ni)
         return scores, counts
 
     def _score_locked(self, ref_indptr, ref_items, ref_vals, tgt_indptr, tgt_items, max_nbrs, min_nbrs):
