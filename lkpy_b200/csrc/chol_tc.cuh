@@ -378,25 +378,36 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
         if (elect_one()) {
             tmem_fence_after();
             const int c0 = 16 * (j + 1);
-            const uint32_t idesc = IDESC_TF32 | ((uint32_t)((64 - c0) >> 3) << 17);
-            {
-                const int s = warp_u;
-                const uint32_t d = tmem_base + ((uint32_t)((s & 1) * 16) << 16) + (uint32_t)((s >> 1) * 64 + c0);
-                const uint32_t hi = smem_u32(ws.tiles + (s * 2) * TILE_BYTES);
-                const uint32_t lo = hi + TILE_BYTES;
-                const uint32_t boff = (uint32_t)(c0 >> 3) * 512;  // B starts at row c0
+            const int s = warp_u;
+            const uint32_t d = tmem_base + ((uint32_t)((s & 1) * 16) << 16) + (uint32_t)((s >> 1) * 64 + c0);
+            const uint32_t hi = smem_u32(ws.tiles + (s * 2) * TILE_BYTES);
+            const uint32_t lo = hi + TILE_BYTES;
+            // D[:, c .. c + n) -= X X[c .. c + n)^T as hi.hi + hi.lo + lo.hi over the two K = 8 slices
+            auto update = [&](const int c, const int n) {
+                const uint32_t idesc = IDESC_TF32 | ((uint32_t)(n >> 3) << 17);
+                const uint32_t boff = (uint32_t)(c >> 3) * 512;  // B starts at row c
 #pragma unroll
                 for (int kk = 0; kk < 2; kk++) {
                     const uint64_t a_hi = DESC | (uint64_t)(((hi + kk * 256) >> 4) & 0x3fffu);
                     const uint64_t a_lo = DESC | (uint64_t)(((lo + kk * 256) >> 4) & 0x3fffu);
                     const uint64_t b_hi = DESC | (uint64_t)(((hi + boff + kk * 256) >> 4) & 0x3fffu);
                     const uint64_t b_lo = DESC | (uint64_t)(((lo + boff + kk * 256) >> 4) & 0x3fffu);
-                    umma_tf32(d, a_hi, b_hi, idesc);
-                    umma_tf32(d, a_hi, b_lo, idesc);
-                    umma_tf32(d, a_lo, b_hi, idesc);
+                    umma_tf32(d + (uint32_t)(c - c0), a_hi, b_hi, idesc);
+                    umma_tf32(d + (uint32_t)(c - c0), a_hi, b_lo, idesc);
+                    umma_tf32(d + (uint32_t)(c - c0), a_lo, b_hi, idesc);
                 }
+            };
+            if (GJ) {
+                update(c0, 64 - c0);
+                umma_commit(bar);
+            } else {
+                // look-ahead: the 16 columns the next step works on (its diagonal block and triangular solves)
+                // first, and the barrier after them; the rest of the trailing update runs in their shadow (it
+                // is complete before the next step's commit: a commit covers everything its thread issued)
+                update(c0, 16);
+                umma_commit(bar);
+                if (c0 + 16 < 64) update(c0 + 16, 64 - c0 - 16);
             }
-            umma_commit(bar);
         }
         __syncwarp();
         // only the warp that factors the next diagonal block needs the updated accumulators now;
