@@ -225,7 +225,9 @@ def _als_parity(tr, di, sh, k, tag, rank, world, dev) -> dict | None:
     out = {"replicas_equal_across_ranks": eq}
     p0, q0 = tp0.cpu().numpy(), tq0.cpu().numpy()
     for which, m, old, other, new in (("user", ui, p0, q0, new_p), ("item", iu, q0, p0, new_q)):
-        rows = parity.sample_als_rows(m.h_indptr, k, engine.DEFAULT_CHUNK_NNZ, n_random=600, seed=7)
+        # rows up to 30 k nonzeros (7 parts): the scalar f64 oracle costs nnz * k^2 per row and all ranks wait for it
+        rows = parity.sample_als_rows(m.h_indptr, k, engine.DEFAULT_CHUNK_NNZ, n_random=400, seed=7, max_nnz=30_000,
+                                      n_longest=4, n_split=12)
         got = new[torch.from_numpy(rows).to(dev)].cpu().numpy()
         sub = _host_rows(m, rows)
         out[which] = parity.check_als_half("implicit", sub, np.arange(len(rows)), old[rows], other, got, REG, bf16)

@@ -46,6 +46,22 @@ def _stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale():
         return LIB
+    # one builder at a time: the ranks of a torchrun launch all import this module, and a stale library
+    # must not be rebuilt by eight processes into the same object files
+    import fcntl
+
+    CSRC.joinpath("build").mkdir(exist_ok=True)
+    with open(CSRC / "build" / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():  # another process built it while this one waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> Path:
     nvcc = _nvcc()
     objdir = CSRC / "build"
     objdir.mkdir(exist_ok=True)
@@ -64,8 +80,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(one, SOURCES))
-    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-ccbin", "/usr/bin/g++", "-o", str(LIB), *map(str, objs)]
+    tmp = LIB.with_suffix(".so.tmp")
+    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-ccbin", "/usr/bin/g++", "-o", str(tmp), *map(str, objs)]
     subprocess.run(cmd, check=True, env=env)
+    os.replace(tmp, LIB)  # readers never see a half-written library
     return LIB
 
 

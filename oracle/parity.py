@@ -24,25 +24,29 @@ from lkpy_b200.data import InteractionCSR
 # ---------------------------------------------------------------------------
 
 
-def sample_als_rows(indptr: np.ndarray, k: int, chunk_nnz: int, n_random: int = 1500, seed: int = 0) -> np.ndarray:
+def sample_als_rows(indptr: np.ndarray, k: int, chunk_nnz: int, n_random: int = 1500, seed: int = 0,
+                    max_nnz: int | None = None, n_longest: int = 16, n_split: int = 48) -> np.ndarray:
     """
     Rows of one half-step to check: the longest rows (every row that the plan splits into parts is a
-    candidate; the 16 longest always), up to 64 empty rows, 400 rows shorter than ``k``, and
-    ``n_random`` others — sorted, unique.
+    candidate; the ``n_longest`` longest always), up to 64 empty rows, 400 rows shorter than ``k``, and
+    ``n_random`` others — sorted, unique.  ``max_nnz`` bounds the length of a sampled row (the scalar f64
+    oracle costs nnz * k^2 per row: at 100 M interactions and k = 128 the hottest rows would take minutes).
     """
     rng = np.random.default_rng(seed)
     n = np.diff(np.asarray(indptr, dtype=np.int64))
-    order = np.argsort(-n, kind="stable")
-    picks = [order[:16]]
-    split = np.flatnonzero(n > chunk_nnz)
+    ok = np.ones(len(n), dtype=bool) if max_nnz is None else n <= max_nnz
+    order = np.argsort(-np.where(ok, n, -1), kind="stable")
+    picks = [order[:n_longest]]
+    split = np.flatnonzero((n > chunk_nnz) & ok)
     if len(split):
-        picks.append(rng.choice(split, min(len(split), 48), replace=False))
+        picks.append(rng.choice(split, min(len(split), n_split), replace=False))
     empty = np.flatnonzero(n == 0)
     picks.append(empty[:64])
     short = np.flatnonzero((n > 0) & (n < k))
     if len(short):
         picks.append(rng.choice(short, min(len(short), 400), replace=False))
-    picks.append(rng.choice(len(n), min(len(n), n_random), replace=False))
+    cand = np.flatnonzero(ok)
+    picks.append(rng.choice(cand, min(len(cand), n_random), replace=False))
     return np.unique(np.concatenate(picks)).astype(np.int64)
 
 
