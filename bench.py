@@ -883,7 +883,9 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
         if not args.no_parity:
             from oracle import parity as par
 
-            cs = par.checksum(cols.cpu().numpy(), vals.cpu().numpy(), cnt.cpu().numpy())
+            live = torch.arange(cols.shape[1], device=dev)[None, :] < cnt[:, None]  # padding past a row's count is not data
+            cs = par.checksum(torch.where(live, cols, 0).cpu().numpy(), torch.where(live, vals, 0.0).cpu().numpy(),
+                              cnt.cpu().numpy())
             tt = torch.tensor([cs >> 32, cs & 0xFFFFFFFF], dtype=torch.int64, device=dev)
             lo, hi = tt.clone(), tt.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)

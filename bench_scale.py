@@ -342,7 +342,9 @@ def _knn_parity(plan, d_ui, d_iu, cols, vals, cnt, rank, world, dev) -> dict | N
     from lkpy_b200.data import InteractionCSR
     from oracle import parity
 
-    eq = _equal_across_ranks([cols, vals, cnt], dev, world)
+    # compare the kept neighbours only: positions past a row's count are uninitialised padding
+    mask = torch.arange(cols.shape[1], device=dev)[None, :] < cnt[:, None]
+    eq = _equal_across_ranks([torch.where(mask, cols, 0), torch.where(mask, vals, 0.0), cnt], dev, world)
     if rank != 0:
         return None
     n_items = d_iu.shape[0]

@@ -247,14 +247,31 @@ __device__ __forceinline__ void solve2(const uint32_t tmem_base, float (&yv)[NSY
             const uint32_t bot_d = tmem_base + ((uint32_t)16 << 16) + (uint32_t)(128 * p);  // lanes 16..31
             const uint32_t boff_top = (uint32_t)(c0 >> 3) * 512;        // B = X rows c0.. of the top half
             const uint32_t boff_bot = bot + (uint32_t)(c0 >> 3) * 512;  // B = X rows 64 + c0..
-            if (half == 0) {
-                update(top_d + c0, 0, boff_top, 64 - c0);    // G11[:, c0:] -= Xt Xt[c0:]^T
-                update(bot_d + c0, bot, boff_top, 64 - c0);  // G21[:, c0:] -= Xb Xt[c0:]^T
-                update(bot_d + 64, bot, bot, 64);            // G22        -= Xb Xb^T
-            } else {
-                update(bot_d + 64 + c0, bot, boff_bot, 64 - c0);  // G22[:, c0:] -= Xb Xb[c0:]^T
+            // look-ahead (as in chol_tc.cuh): the 16 columns the next step works on first, the barrier after
+            // them, the rest of the trailing update in their shadow (a later commit of this thread covers it)
+            auto update16 = [&](uint32_t d, uint32_t a_off, uint32_t b_off, int n, bool first) {
+                if (first)
+                    update(d, a_off, b_off, n > 16 ? 16 : n);
+                else if (n > 16)
+                    update(d + 16, a_off, b_off + 2 * 512, n - 16);
+            };
+            for (int pass = 0; pass < 2; pass++) {
+                const bool first = pass == 0;
+                if (half == 0) {
+                    if (jb < 3) {
+                        // next step: block column jb + 1 of the left panel (top and bottom rows)
+                        update16(top_d + c0, 0, boff_top, 64 - c0, first);    // G11[:, c0:] -= Xt Xt[c0:]^T
+                        update16(bot_d + c0, bot, boff_top, 64 - c0, first);  // G21[:, c0:] -= Xb Xt[c0:]^T
+                        if (!first) update(bot_d + 64, bot, bot, 64);         // G22        -= Xb Xb^T
+                    } else {
+                        // jb == 3: the next step starts on G22 — its first 16 columns are the urgent part
+                        update16(bot_d + 64, bot, bot, 64, first);
+                    }
+                } else {
+                    update16(bot_d + 64 + c0, bot, boff_bot, 64 - c0, first);  // G22[:, c0:] -= Xb Xb[c0:]^T
+                }
+                if (first) umma_commit(bar);
             }
-            umma_commit(bar);
         }
         __syncwarp();
         // only the warp that factors the next diagonal block needs the updated accumulators now
