@@ -73,6 +73,25 @@ def _equal_across_ranks(tensors, dev, world: int) -> bool:
     return bool(torch.equal(lo, hi))
 
 
+def _inputs_equal_across_ranks(tensors, dev, world: int) -> bool:
+    """Every rank generates the workload itself: check they all generated the same one (integer sums of
+    the raw bits, whole and over two strided slices — no large temporaries)."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return True
+    sig = []
+    for t in tensors:
+        b = t.view(torch.int32) if t.dtype == torch.float32 else t
+        sig += [b.sum(dtype=torch.int64), b[1::2].sum(dtype=torch.int64), b[::3].sum(dtype=torch.int64)]
+    sig = torch.stack(sig)
+    lo, hi = sig.clone(), sig.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi))
+
+
 def run(args, rank: int, world: int, dev, peak: float, peak_src: str) -> dict | None:
     return run_als(args, rank, world, dev, peak, peak_src) if args.workload == "als100m" else run_knn(
         args, rank, world, dev, peak, peak_src)  # fmt: skip
@@ -103,6 +122,8 @@ def run_als(args, rank, world, dev, peak, peak_src) -> dict | None:
     t0 = time.time()
     u, i, r = prep.synth_interactions_device(sh["n_users"], sh["n_items"], sh["nnz"], device=dev)
     di = prep.DeviceInteractions(u, i, r, sh["n_users"], sh["n_items"])
+    if not _inputs_equal_across_ranks([u, i, r], dev, world):
+        raise RuntimeError("als100m: the ranks generated different interaction matrices")
     torch.cuda.synchronize()
     log(f"[scale] als100m data on device: {sh['n_users']}x{sh['n_items']}, nnz {di.nnz} ({time.time() - t0:.1f}s)")
     results, parity = {}, {}
@@ -263,6 +284,8 @@ def run_knn(args, rank, world, dev, peak, peak_src) -> dict | None:
     nnz = int(u.numel())
     torch.cuda.synchronize()
     t_gen = time.time() - t0
+    if not _inputs_equal_across_ranks([u, i, r], dev, world):
+        raise RuntimeError("knn1b: the ranks generated different interaction matrices")
     t0 = time.time()
     d_ui, d_iu, _means = prep.knn_item_matrices_device(u, i, r, sh["n_users"], sh["n_items"], True)
     del u, i, r

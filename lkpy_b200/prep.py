@@ -114,12 +114,16 @@ def synth_interactions_device(
     device = device or _lib.require_device()
     gen = torch.Generator(device=device)
     gen.manual_seed(int(seed))
-    uw = torch.exp(torch.randn(n_users, generator=gen, device=device, dtype=torch.float64) * 1.25)
-    ucdf = torch.cumsum(uw / uw.sum(), 0)
-    iw = (torch.arange(n_items, device=device, dtype=torch.float64) + 20.0) ** -1.05
-    icdf = torch.cumsum(iw / iw.sum(), 0)
-    ucdf[-1] = 1.0
-    icdf[-1] = 1.0
+    # the two CDFs are accumulated on the host: a CUDA prefix sum of floats is not run-to-run (or
+    # rank-to-rank) reproducible, and every rank of a sharded run must generate the same matrix
+    def _cdf(w: torch.Tensor) -> torch.Tensor:
+        h = w.cpu().numpy()
+        c = np.cumsum(h / h.sum())
+        c[-1] = 1.0
+        return torch.from_numpy(c).to(device)
+
+    ucdf = _cdf(torch.exp(torch.randn(n_users, generator=gen, device=device, dtype=torch.float64) * 1.25))
+    icdf = _cdf((torch.arange(n_items, dtype=torch.float64) + 20.0) ** -1.05)
     perm = torch.randperm(n_items, generator=gen, device=device)
     want = int(np.ceil(1.25 * nnz))
     keys = torch.empty(0, dtype=torch.int64, device=device)
@@ -149,7 +153,7 @@ def synth_interactions_device(
     users = (keys // n_items).to(torch.int32)
     items = (keys % n_items).to(torch.int32)
     del keys
-    pmf = torch.tensor(ML_RATING_PMF / ML_RATING_PMF.sum(), device=device, dtype=torch.float64)
-    rv = torch.searchsorted(torch.cumsum(pmf, 0), torch.rand(nnz, generator=gen, device=device, dtype=torch.float64), right=True)
+    pcdf = torch.from_numpy(np.cumsum(ML_RATING_PMF / ML_RATING_PMF.sum())).to(device)
+    rv = torch.searchsorted(pcdf, torch.rand(nnz, generator=gen, device=device, dtype=torch.float64), right=True)
     ratings = torch.tensor(ML_RATING_VALUES, device=device)[rv.clamp_max(len(ML_RATING_VALUES) - 1)]
     return users, items, ratings
