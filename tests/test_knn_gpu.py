@@ -319,3 +319,32 @@ def test_accel_api_mirror(cuda_lib, ml_small):
     bad = pa.ListArray.from_arrays(pa.array([0, 1], type=pa.int32()), pa.array([0.5], type=pa.float64()))
     with pytest.raises(TypeError):
         accel.as_host_csr(bad)
+
+
+def test_build_cancel_flag_and_task(cuda_lib, ml_small):
+    """The build stops handing out work when the device cancel flag is up (tasks/mod.rs:84-90 through
+    item_train.rs's CancelAdapter): a flag raised before the launch leaves every row empty, a task cancelled
+    before `invoke` raises, and a finished task reports (n_items, n_items)."""
+    from lkpy_b200 import accel
+
+    ui, iu, _ = data.knn_item_matrices(ml_small, True)
+    dev = _lib.require_device()
+    plan = engine.KnnBuildPlan.create(engine.DeviceCSR.from_host(ui, dev), engine.DeviceCSR.from_host(iu, dev))
+    plan.cancel = torch.ones(1, dtype=torch.int32, device=dev)
+    _cols, _vals, cnt = plan.build_topk(1e-6, 20)
+    torch.cuda.synchronize()
+    assert int(cnt.sum().item()) == 0
+    plan.cancel.zero_()
+    _cols, _vals, cnt = plan.build_topk(1e-6, 20)
+    torch.cuda.synchronize()
+    assert int(cnt.sum().item()) == oracle.knn_build(ui, iu, 1e-6, 20).nnz
+
+    shape = (ml_small.n_users, ml_small.n_items)
+    task = accel.knn.compute_similarities(ui, iu, shape, 1e-6, 20)
+    assert task.current_progress() == (0, ml_small.n_items)
+    task.cancel()
+    with pytest.raises(RuntimeError, match="cancelled"):
+        task.invoke()
+    task = accel.knn.compute_similarities(ui, iu, shape, 1e-6, 20)
+    task.invoke()
+    assert task.current_progress() == (ml_small.n_items, ml_small.n_items)
