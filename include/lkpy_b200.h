@@ -127,7 +127,7 @@ typedef struct lk_als_args {
     int32_t vals_uniform;    /* 1 when every d_vals entry equals uniform_val (implicit feedback without
                                 ratings): lets the Gram run on the tensor cores as v * M^T M */
     float uniform_val;
-    unsigned long long *d_prof; /* optional [8] per-phase SM-cycle counters (diagnostics), or NULL */
+    unsigned long long *d_prof; /* optional [16] per-phase SM-cycle counters (diagnostics), or NULL */
     /* Cooperative cancel (the role of CancelAdapter, src/accel/als/implicit.rs:72-73, tasks/mod.rs:62-106):
      * optional device flag, read (uncached) every time a CTA fetches work; once non-zero no further rows
      * are started — rows already solved keep their new values, the rest their old ones.  Progress =

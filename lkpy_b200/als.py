@@ -266,12 +266,12 @@ class ALSTrainerBase(ModelTrainer):
         return self.scorer.config
 
     def _chunk_nnz(self, k: int) -> int:
-        tcx = (k == 64 and self.config.gather_dtype == "float32") or (
-            self.MODE == _lib.LK_ALS_IMPLICIT and getattr(self.config, "use_ratings", False)
-        )
-        if tcx or (k == 128 and self.config.gather_dtype == "bfloat16"):
+        weighted = self.MODE == _lib.LK_ALS_IMPLICIT and getattr(self.config, "use_ratings", False)
+        bf16_uniform = self.config.gather_dtype == "bfloat16" and not weighted
+        if (k == 64 and not bf16_uniform) or k == 128:
             # shorter parts where a tensor-core accumulator would otherwise take hundreds of round-toward-zero
-            # additions (engine.TF32_CHUNK_NNZ): at k = 128 the 100 M-interaction item rows reach 1e-4 otherwise
+            # additions (engine.TF32_CHUNK_NNZ): the tf32 paths make three per 8 rows, and at k = 128 the
+            # 100 M-interaction item rows reach 1e-4 on the bf16 path otherwise
             return engine.TF32_CHUNK_NNZ
         return engine.DEFAULT_CHUNK_NNZ
 
@@ -332,9 +332,10 @@ class ALSTrainerBase(ModelTrainer):
         uniform = self.MODE != _lib.LK_ALS_IMPLICIT or not getattr(self.config, "use_ratings", False)
         if on and k == 64 and self.bf16 and uniform:
             return "als_tc_kernel"
-        if on and k == 64 and _lib.get_option("LK_ALS_TF32") != 0:
+        tf32 = _lib.get_option("LK_ALS_TF32") != 0
+        if on and k == 64 and tf32:
             return "als_tcx_kernel"
-        if on and k == 128 and self.bf16 and uniform:
+        if on and k == 128 and ((self.bf16 and uniform) or tf32):
             return "als_tc128_kernel"
         return "als_half_kernel"
 

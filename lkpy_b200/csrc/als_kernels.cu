@@ -449,7 +449,7 @@ __global__ void otor_reduce_kernel(const float *__restrict__ partial, int nblock
 
 int launch_als_tc(const lk_als_args &a, cudaStream_t st);   // als_tc.cu  (bf16 rows, uniform weights)
 int launch_als_tcx(const lk_als_args &a, cudaStream_t st);  // als_tcx.cu (fp32 rows / non-uniform weights, tf32 x3)
-int launch_als_tc128(const lk_als_args &a, cudaStream_t st);  // als_tc128.cu (k = 128, bf16 rows, uniform weights)
+int launch_als_tc128(const lk_als_args &a, cudaStream_t st);  // als_tc128.cu (k = 128: kind::f16 for bf16 rows with uniform weights, tf32 x3 otherwise)
 
 static int pad_features(int k) { return k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : -1; }
 

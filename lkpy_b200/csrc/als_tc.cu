@@ -58,7 +58,7 @@ static_assert(WARP_BYTES >= NSTAGE * STAGE_BYTES && WARP_BYTES % 1024 == 0, "sta
 constexpr int TMEM_COLS = 128;
 constexpr int SLOTF = KP * KP + KP;
 constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + WARPS * WARP_BYTES + 2 * WARPS * KP * 4 +
-                           (WARPS * NSTAGE + WARPS + 1) * 8 + 16 + 64 * 4 + 128 + 256 /* ones tile */;
+                           (WARPS * NSTAGE + WARPS + 2) * 8 + 16 + 64 * 4 + 128 + 256 /* ones tile */;
 static_assert(ctc::WS_BYTES <= WARPS * WARP_BYTES, "the tensor-core solve workspace aliases the stage rings");
 constexpr int TMEM_Y_COLS = 32;  // second allocation: 64x8 right-hand-side accumulators
 
@@ -81,7 +81,7 @@ using tcd::DESC_LBO;
 // by one warp each (als_common.cuh).
 // GJ (with TCS): block Gauss-Jordan variant of the tensor-core solve (chol_tc.cuh).
 template <int MODE, bool TCS, bool GJ = false>
-__global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const int interleave)
+__global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const int interleave, const int flags)
 {
     using namespace tc;
     extern __shared__ unsigned char smem_raw[];
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     uint64_t *stage_free = bars + warp * NSTAGE;  // [NSTAGE] of this warp
     uint64_t *acc_full = bars + WARPS * NSTAGE;   // [WARPS]
     uint64_t *solve_bar = acc_full + WARPS;       // trailing-update MMAs of the tensor-core solve
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(solve_bar + 1);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(solve_bar + 2);  // solve_bar[1]: second pass of the updates
     int *s_misc = reinterpret_cast<int *>(s_tmem + 4);  // [0] group, then per-chunk metadata [8 + 8*c ...]
     unsigned char *ones_tile = reinterpret_cast<unsigned char *>(s_misc + 64);
     ones_tile += (128u - (smem_u32(ones_tile) & 127u)) & 127u;
@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
     if (tid == 0) {
         for (int i = 0; i < WARPS * NSTAGE + WARPS; i++) mbar_init(&bars[i], 1);
         mbar_init(solve_bar, 4);
+        mbar_init(solve_bar + 1, 4);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -201,8 +202,10 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
         nparts = __shfl_sync(FULL, nparts, 0), slot0 = __shfl_sync(FULL, slot0, 0);
         part = __shfl_sync(FULL, part, 0), split_idx = __shfl_sync(FULL, split_idx, 0);
         const bool has_gram = active && len > 0;
+        // the row's full length is only needed for the explicit regulariser (reg * n): in implicit mode the
+        // two dependent loads would sit between the chunk record and the first index loads for nothing
         int n_row = 0;
-        if (active) n_row = __ldg(a.d_indptr + row + 1) - __ldg(a.d_indptr + row);
+        if (MODE == LK_ALS_EXPLICIT && active) n_row = __ldg(a.d_indptr + row + 1) - __ldg(a.d_indptr + row);
         if (lane == 0) {
             int *m = s_misc + 8 + 8 * warp;
             m[0] = has_gram ? 1 : 0;
@@ -225,11 +228,20 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
 #pragma unroll
             for (int s = 0; s < NSTAGE; s++) vst[s] = 0.0f;
 
+            // the indices are read once: with flags bit 0 they stream past L1 (no-allocate), which keeps the
+            // 16 KB OtOr matrix of the accumulator preload and the chunk records resident there; the values
+            // are not read at all when the right-hand side goes through the tensor cores (uniform weights)
+            const bool stream = (flags & 1) != 0;
             auto fetch = [&](int it, int &c, float &v) {
                 const int idx = it * STAGE_ROWS + lane;
                 if (it < n_it && idx < len) {
-                    c = __ldg(cols + idx);
-                    v = __ldg(vals + idx);
+                    if (stream) {
+                        c = ld_stream_s32(cols + idx);
+                        v = ymma ? 0.0f : ld_stream_f32(vals + idx);
+                    } else {
+                        c = __ldg(cols + idx);
+                        v = __ldg(vals + idx);
+                    }
                 } else {
                     c = 0;
                     v = 0.0f;
@@ -353,6 +365,9 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             // ------------------------------------------------------------------
             // phase 2': finish the systems in place in TMEM (A = v*G + OtOr, or G + reg*n*I)
             // ------------------------------------------------------------------
+            // next group: every thread has read s_misc[0] (barrier at the loop top), so it can be replaced
+            // now; the value is visible to all warps after the barrier that closes this phase
+            if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);
             const ctc::Workspace ws = ctc::carve(base);  // aliases the stage rings: all their MMAs have completed
             const int r16 = lane & 15, hh = lane >> 4;
             const int gi = 16 * warp + r16;  // Gram row / feature held by this lane (of system 2p + hh)
@@ -491,7 +506,6 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
             // ------------------------------------------------------------------
             // phase 3': blocked Cholesky on the tensor cores, write-back
             // ------------------------------------------------------------------
-            if (tid == 0) s_misc[0] = fetch_work(a.d_work_counter, a.d_cancel);  // next group, read after the closing barrier
             if (solve_mask) {
                 // old values of the rows about to be written: fetched before the solve, not waited for after it
                 float xold[2] = {0.0f, 0.0f};
@@ -502,6 +516,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                 }
                 ctc::solve4<false, GJ>(tmem_base, yv, ws, solve_bar, solve_par, tid);
                 __syncthreads();  // pivot flags
+                prof(7);
                 float dpart[2] = {0.0f, 0.0f};
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
@@ -538,6 +553,7 @@ __global__ void __launch_bounds__(tc::NT, 3) als_tc_kernel(lk_als_args a, const 
                         a.d_replicas[rr][(size_t)(a.replica_row0 + row) * k + i] = 0.0f;
                 }
             }
+            prof(8);
             if constexpr (PRELOAD) preload_otor();  // accumulators of the next group (this warp's rows)
             prof(5);
             __syncthreads();  // the workspace aliases the stage rings of the next group
@@ -722,7 +738,7 @@ int launch_als_tc(const lk_als_args &a, cudaStream_t st)
     const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * occ, groups));
     auto launch = [&](auto kern) -> int {
         LK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave);
+        kern<<<(unsigned)grid, tc::NT, smem, st>>>(a, interleave, opt.als_flags);
         return LK_OK;
     };
     // LK_ALS_GJ=1: block Gauss-Jordan instead of blocked Cholesky + block back substitution (experiment)

@@ -1,8 +1,12 @@
 // als_tc128.cu — ALS half-epoch at k = 128 on the tensor cores (BASELINE configs[3]: 100 M interactions,
-// features = 128): bf16 gathered rows, unweighted (explicit) or uniformly weighted (implicit without
-// ratings) Gram, the 128x128 systems solved in TMEM (chol_tc128.cuh).  Same contract as
+// features = 128), the 128x128 systems solved in TMEM (chol_tc128.cuh).  Same contract as
 // als_half_kernel<128, ...> (reference src/accel/als/implicit.rs:87-125, explicit.rs:80-119,
-// solve.rs:65-106), which stays the path for everything else at this size.
+// solve.rs:65-106), which keeps what this kernel does not take (negative or zero confidences).
+// Two gather paths, one per operand type:
+//   * bf16 rows, unweighted (explicit) or uniformly weighted (implicit without ratings): exact bf16 products,
+//     tcgen05.mma.kind::f16 — described below;
+//   * fp32 rows (the reference's own arithmetic) and/or per-nonzero confidences (use_ratings=True): the
+//     tf32 hi/lo split of als_tcx.cu at twice the width — see `gather_tf32`.
 //
 // A 128x128 lower triangle is three M=64 accumulators (chol_tc128.cuh): with the gathered row split into
 // its two 64-feature halves m = [m0 | m1] (each exactly one 128-byte row of an MN-major SWIZZLE_128B tile),
@@ -34,14 +38,39 @@ constexpr int NSTAGE = 3;
 constexpr int ATOM_BYTES = STAGE_ROWS * 128;    // 16 rows x 64 bf16
 constexpr int STAGE_BYTES = 2 * ATOM_BYTES;     // features 0..63 | 64..127
 constexpr int RING_BYTES = NSTAGE * STAGE_BYTES;  // per gathering warp: 12 KB
+// tf32 path: 8 rows per stage; K-major no-swizzle tiles of 64 features x 8 rows (als_tcx.cu's layout: the
+// 8-feature groups 272 bytes apart), four per stage: features 0..63 hi, lo, features 64..127 hi, lo
+constexpr int X_STAGE_ROWS = 8;
+constexpr int X_GROUP_STRIDE = 272;
+constexpr int X_TILE_BYTES = 8 * X_GROUP_STRIDE;
+constexpr int X_STAGE_BYTES = 4 * X_TILE_BYTES;
+constexpr int X_RING_BYTES = NSTAGE * X_STAGE_BYTES;  // per gathering warp: 25.5 KB
+constexpr uint32_t X_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
+constexpr uint64_t X_DESC = (uint64_t(128 >> 4) << 16) | (uint64_t(X_GROUP_STRIDE >> 4) << 32) | (1ull << 46);
 constexpr int TMEM_COLS = 256;
 constexpr int SLOTF = KP * KP + KP;
 constexpr int WS_ALIGNED = (ctc128::WS_BYTES + 1023) & ~1023;
-constexpr int UNION_BYTES = WS_ALIGNED > NSYS * RING_BYTES ? WS_ALIGNED : NSYS * RING_BYTES;
-constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + UNION_BYTES + NSYS * KP * 4 + (NSYS * NSTAGE + NSYS + 1) * 8 + 16 + 64 * 4;
+static_assert(X_RING_BYTES >= RING_BYTES && X_RING_BYTES % 16 == 0, "the union is sized for the larger ring");
+constexpr int UNION_BYTES = WS_ALIGNED > NSYS * X_RING_BYTES ? WS_ALIGNED : NSYS * X_RING_BYTES;
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + UNION_BYTES + NSYS * KP * 4 + (NSYS * NSTAGE + NSYS + 2) * 8 + 16 + 64 * 4;
 }  // namespace t128
 
-template <int MODE>
+// 4 consecutive features (quad q of 32) of a gathered 128-feature row as f32
+__device__ __forceinline__ float4 load_quad128(const float *other, int row, int q)
+{
+    return __ldg(reinterpret_cast<const float4 *>(other + (size_t)row * t128::KP) + q);
+}
+__device__ __forceinline__ float4 load_quad128(const __nv_bfloat16 *other, int row, int q)
+{
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(other + (size_t)row * t128::KP) + q);
+    return make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
+                       __uint_as_float(t.y & 0xffff0000u));
+}
+
+// MODE: LK_ALS_IMPLICIT / LK_ALS_EXPLICIT.  ET: float or __nv_bfloat16 rows of `other`.  WEIGHTED: implicit
+// mode with per-nonzero confidences (z = sqrt(v) o, A = OtOr + Z^T Z); otherwise the Gram is unweighted and
+// scaled by the uniform confidence (implicit) or not at all (explicit).
+template <int MODE, typename ET, bool WEIGHTED>
 __global__ void __launch_bounds__(t128::NT, 2) als_tc128_kernel(lk_als_args a)
 {
     using namespace t128;
@@ -53,18 +82,21 @@ __global__ void __launch_bounds__(t128::NT, 2) als_tc128_kernel(lk_als_args a)
     uint64_t *bars = reinterpret_cast<uint64_t *>(ys_all + NSYS * KP);
     uint64_t *acc_full = bars + NSYS * NSTAGE;
     uint64_t *solve_bar = acc_full + NSYS;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(solve_bar + 1);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(solve_bar + 2);  // solve_bar[1]: second pass of the updates
     int *s_misc = reinterpret_cast<int *>(s_tmem + 4);
 
-    const __nv_bfloat16 *__restrict__ other = reinterpret_cast<const __nv_bfloat16 *>(a.d_other);
+    const ET *__restrict__ other = reinterpret_cast<const ET *>(a.d_other);
     constexpr int k = KP;
     constexpr bool IMPLICIT = MODE == LK_ALS_IMPLICIT;
-    const float scale = IMPLICIT ? a.uniform_val : 1.0f;  // the in-TMEM system is A / scale
+    constexpr bool TF32 = WEIGHTED || sizeof(ET) == 4;  // bf16 rows with uniform weights take the kind::f16 path
+    // A = OtOr + scale * G; the in-TMEM system is A / scale, solved against y / scale
+    const float scale = (IMPLICIT && !WEIGHTED) ? a.uniform_val : 1.0f;
     const float rscale = 1.0f / scale;
 
     if (tid == 0) {
         for (int i = 0; i < NSYS * NSTAGE + NSYS; i++) mbar_init(&bars[i], 1);
         mbar_init(solve_bar, ctc128::NSYS);
+        mbar_init(solve_bar + 1, ctc128::NSYS);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -140,7 +172,140 @@ __global__ void __launch_bounds__(t128::NT, 2) als_tc128_kernel(lk_als_args a)
         // ------------------------------------------------------------------
         // phase 1 (warps 0, 1): rows -> registers -> (column sums, swizzled bf16 tiles) -> tcgen05.mma
         // ------------------------------------------------------------------
-        if (has_gram) {
+        if constexpr (TF32) {
+          if (has_gram) {
+            // gather_tf32: a lane is (row quad rq, feature quad fq) of the 8 x 128 stage and holds a 4 x 4
+            // micro-block of each 64-feature half: 8 LDG.128 per stage (4 x LDG.64 for bf16 rows).  The rows are
+            // scaled (sqrt(v) when WEIGHTED), accumulated into the right-hand side on the way, split exactly into
+            // hi (top 19 bits, a tf32 number) and lo = z - hi, and stored transposed as 16-byte K-vectors.  Per
+            // 8 rows: G11 += Z0^T Z0, G21 += Z1^T Z0, G22 += Z1^T Z1, each as hi.hi + hi.lo + lo.hi — nine
+            // tcgen05.mma.kind::tf32 (M = N = 64, K = 8).
+            unsigned char *ring = base + warp * X_RING_BYTES;
+            uint64_t *stage_free = bars + warp * NSTAGE;
+            const int n_it = (len + X_STAGE_ROWS - 1) / X_STAGE_ROWS;
+            const int32_t *cols = a.d_cols + begin;
+            const float *vals = a.d_vals + begin;
+            const uint32_t top_d = tmem_base + (uint32_t)(128 * warp);
+            const uint32_t bot_d = tmem_base + ((uint32_t)16 << 16) + (uint32_t)(128 * warp);
+            const int rq = lane >> 4, fq = lane & 15;
+            const uint32_t st_off = (uint32_t)((fq >> 1) * X_GROUP_STRIDE + rq * 128 + (fq & 1) * 64);
+            float4 ysum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+
+            constexpr int IDX_AHEAD = 4;
+            int ci_[IDX_AHEAD][4];
+            float vi_[IDX_AHEAD][4];
+            auto load_idx = [&](int it, int (&c)[4], float (&v)[4]) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int idx = it * X_STAGE_ROWS + 4 * rq + i;
+                    const bool in = it < n_it && idx < len;
+                    c[i] = in ? __ldg(cols + idx) : -1;
+                    v[i] = in ? __ldg(vals + idx) : 0.0f;
+                }
+            };
+            auto load_rows = [&](const int (&c)[4], float4 (&x)[2][4]) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; h2++)
+                        x[h2][i] = c[i] >= 0 ? load_quad128(other, c[i], fq + 16 * h2) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            float4 xr[2][2][4];
+#pragma unroll
+            for (int u = 0; u < IDX_AHEAD; u++) load_idx(u, ci_[u], vi_[u]);
+            load_rows(ci_[0], xr[0]);
+            load_rows(ci_[1], xr[1]);
+
+            auto consume = [&](int it, float4 (&x)[2][4], float (&v)[4]) {
+                const int s = it % NSTAGE;
+                if (it >= NSTAGE) mbar_wait(&stage_free[s], ((free_par >> s) & 1u) ^ 1u);
+                unsigned char *st = ring + s * X_STAGE_BYTES + st_off;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    // right-hand side: implicit y += (v + 1) o, explicit y += v o (rows past the end carry x = 0)
+                    const float w = IMPLICIT ? v[i] + 1.0f : v[i];
+                    float sv = 1.0f;
+                    if constexpr (WEIGHTED) sv = sqrtf(v[i]);
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; h2++) {
+                        ysum[h2].x = fmaf(w, x[h2][i].x, ysum[h2].x), ysum[h2].y = fmaf(w, x[h2][i].y, ysum[h2].y);
+                        ysum[h2].z = fmaf(w, x[h2][i].z, ysum[h2].z), ysum[h2].w = fmaf(w, x[h2][i].w, ysum[h2].w);
+                        if constexpr (WEIGHTED)
+                            x[h2][i].x *= sv, x[h2][i].y *= sv, x[h2][i].z *= sv, x[h2][i].w *= sv;
+                    }
+                }
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    unsigned char *thi = st + (2 * h2) * X_TILE_BYTES;
+                    unsigned char *tlo = thi + X_TILE_BYTES;
+                    // transposed stores: feature 4*fq + j, rows 4*rq .. 4*rq+3 -> one 16-byte K-vector
+                    auto put = [&](int j, float e0, float e1, float e2, float e3) {
+                        float4 hi, lo;
+                        hi.x = __uint_as_float(__float_as_uint(e0) & 0xffffe000u);
+                        hi.y = __uint_as_float(__float_as_uint(e1) & 0xffffe000u);
+                        hi.z = __uint_as_float(__float_as_uint(e2) & 0xffffe000u);
+                        hi.w = __uint_as_float(__float_as_uint(e3) & 0xffffe000u);
+                        lo.x = e0 - hi.x, lo.y = e1 - hi.y, lo.z = e2 - hi.z, lo.w = e3 - hi.w;
+                        *reinterpret_cast<float4 *>(thi + j * 16) = hi;
+                        *reinterpret_cast<float4 *>(tlo + j * 16) = lo;
+                    };
+                    put(0, x[h2][0].x, x[h2][1].x, x[h2][2].x, x[h2][3].x);
+                    put(1, x[h2][0].y, x[h2][1].y, x[h2][2].y, x[h2][3].y);
+                    put(2, x[h2][0].z, x[h2][1].z, x[h2][2].z, x[h2][3].z);
+                    put(3, x[h2][0].w, x[h2][1].w, x[h2][2].w, x[h2][3].w);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (ctc::elect_one()) {
+                    tmem_fence_after();
+                    const uint32_t t0 = smem_u32(ring + s * X_STAGE_BYTES);
+                    auto dsc = [&](int tile) { return X_DESC | (uint64_t)(((t0 + tile * X_TILE_BYTES) >> 4) & 0x3fffu); };
+                    const uint64_t h0 = dsc(0), l0 = dsc(1), h1 = dsc(2), l1 = dsc(3);
+                    const uint32_t acc = (IMPLICIT || it > 0) ? 1u : 0u;
+                    umma_tf32_acc(top_d, h0, h0, X_IDESC, acc);  // G11 += Z0^T Z0
+                    umma_tf32_acc(top_d, h0, l0, X_IDESC, 1u);
+                    umma_tf32_acc(top_d, l0, h0, X_IDESC, 1u);
+                    umma_tf32_acc(bot_d, h1, h0, X_IDESC, acc);  // G21 += Z1^T Z0
+                    umma_tf32_acc(bot_d, h1, l0, X_IDESC, 1u);
+                    umma_tf32_acc(bot_d, l1, h0, X_IDESC, 1u);
+                    umma_tf32_acc(bot_d + 64, h1, h1, X_IDESC, acc);  // G22 += Z1^T Z1
+                    umma_tf32_acc(bot_d + 64, h1, l1, X_IDESC, 1u);
+                    umma_tf32_acc(bot_d + 64, l1, h1, X_IDESC, 1u);
+                    umma_commit(&stage_free[s]);
+                    if (it == n_it - 1) umma_commit(&acc_full[warp]);
+                }
+                free_par ^= (1u << s);
+                __syncwarp();
+            };
+            for (int it0 = 0; it0 < n_it; it0 += IDX_AHEAD) {
+#pragma unroll
+                for (int u = 0; u < IDX_AHEAD; u++) {
+                    const int it = it0 + u;
+                    if (it < n_it) {
+                        consume(it, xr[u & 1], vi_[u]);
+                        load_rows(ci_[(u + 2) % IDX_AHEAD], xr[u & 1]);  // rows of stage it + 2
+                        load_idx(it + IDX_AHEAD, ci_[u], vi_[u]);        // indices of stage it + IDX_AHEAD
+                    }
+                }
+            }
+            // right-hand side of the chunk: fold the two row quads; lanes 0..15 hold features 4*fq.. of each half
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+                ysum[h2].x += __shfl_xor_sync(FULL, ysum[h2].x, 16), ysum[h2].y += __shfl_xor_sync(FULL, ysum[h2].y, 16);
+                ysum[h2].z += __shfl_xor_sync(FULL, ysum[h2].z, 16), ysum[h2].w += __shfl_xor_sync(FULL, ysum[h2].w, 16);
+                if (lane < 16) {
+                    if (nparts == 1)
+                        *reinterpret_cast<float4 *>(ys_all + warp * KP + 64 * h2 + 4 * fq) = ysum[h2];
+                    else
+                        __stcg(reinterpret_cast<float4 *>(a.d_partials + (size_t)(slot0 + part) * SLOTF + KP * KP) +
+                                   16 * h2 + fq,
+                               ysum[h2]);
+                }
+            }
+          }
+        } else if (has_gram) {
+            const __nv_bfloat16 *other16 = reinterpret_cast<const __nv_bfloat16 *>(a.d_other);
             unsigned char *ring = base + warp * RING_BYTES;
             uint64_t *stage_free = bars + warp * NSTAGE;
             const int n_it = (len + STAGE_ROWS - 1) / STAGE_ROWS;
@@ -169,7 +334,7 @@ __global__ void __launch_bounds__(t128::NT, 2) als_tc128_kernel(lk_als_args a)
 #pragma unroll
                 for (int i = 0; i < STAGE_ROWS; i++) {
                     const int ci_ = __shfl_sync(FULL, c, i);
-                    x[i] = ci_ >= 0 ? __ldg(reinterpret_cast<const uint2 *>(other + (size_t)ci_ * k) + lane) : make_uint2(0u, 0u);
+                    x[i] = ci_ >= 0 ? __ldg(reinterpret_cast<const uint2 *>(other16 + (size_t)ci_ * k) + lane) : make_uint2(0u, 0u);
                 }
             };
             uint2 xr[2][STAGE_ROWS];
@@ -409,9 +574,16 @@ __global__ void __launch_bounds__(t128::NT, 2) als_tc128_kernel(lk_als_args a)
 int launch_als_tc128(const lk_als_args &a, cudaStream_t st)
 {
     const Options &opt = options();
-    if (a.k != t128::KP || a.other_dtype != LK_DTYPE_BF16 || opt.als_tcs == 0) return 1;
-    if (a.mode == LK_ALS_IMPLICIT && (!a.vals_uniform || !(fabsf(a.uniform_val) > 1e-20f))) return 1;
+    if (a.k != t128::KP || opt.als_tcs == 0) return 1;
     if (reinterpret_cast<uintptr_t>(a.d_other) % 16 != 0) return 1;
+    const bool f32 = a.other_dtype == LK_DTYPE_F32;
+    const bool implicit = a.mode == LK_ALS_IMPLICIT;
+    const bool weighted = implicit && !a.vals_uniform;
+    if ((f32 || weighted) && opt.als_tf32 == 0) return 1;  // diagnostics: keep these on the SIMT kernel
+    // the weighted Gram uses z = sqrt(v) o: confidences must not be negative (the plan passes the minimum)
+    if (weighted && !(a.uniform_val >= 0.0f)) return 1;
+    // uniform confidence 0: (A / v) is undefined
+    if (implicit && !weighted && !(fabsf(a.uniform_val) > 1e-20f)) return 1;
     const int smem = t128::SMEM_BYTES;
     const int64_t groups = (a.n_chunks + t128::NSYS - 1) / t128::NSYS;
     int occ = 2;  // 256 TMEM columns per CTA
@@ -422,8 +594,18 @@ int launch_als_tc128(const lk_als_args &a, cudaStream_t st)
         kern<<<(unsigned)grid, t128::NT, smem, st>>>(a);
         return LK_OK;
     };
-    const int rc = a.mode == LK_ALS_IMPLICIT ? launch(als_tc128_kernel<LK_ALS_IMPLICIT>)
-                                             : launch(als_tc128_kernel<LK_ALS_EXPLICIT>);
+    int rc;
+    if (implicit) {
+        if (weighted)
+            rc = f32 ? launch(als_tc128_kernel<LK_ALS_IMPLICIT, float, true>)
+                     : launch(als_tc128_kernel<LK_ALS_IMPLICIT, __nv_bfloat16, true>);
+        else
+            rc = f32 ? launch(als_tc128_kernel<LK_ALS_IMPLICIT, float, false>)
+                     : launch(als_tc128_kernel<LK_ALS_IMPLICIT, __nv_bfloat16, false>);
+    } else {
+        rc = f32 ? launch(als_tc128_kernel<LK_ALS_EXPLICIT, float, false>)
+                 : launch(als_tc128_kernel<LK_ALS_EXPLICIT, __nv_bfloat16, false>);
+    }
     if (rc != LK_OK) return rc;
     LK_CUDA_TRY(cudaGetLastError());
     return LK_OK;

@@ -43,28 +43,20 @@ constexpr int TILE_BYTES = 8 * GROUP_STRIDE;        // 64 features x 8 rows of t
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;         // hi, lo
 constexpr int RING_BYTES = NSTAGE * STAGE_BYTES;    // per warp
 constexpr int TMEM_COLS = 128;
+// the block Gauss-Jordan variant of the in-TMEM solve (chol_tc.cuh): ~4 % faster than Cholesky + block back
+// substitution at the same measured accuracy (profiles/r02_experiments.md); als_tc.cu switches by option
+constexpr bool TCX_GJ = true;
 constexpr int SLOTF = KP * KP + KP;
 constexpr int WS_ALIGNED = (ctc::WS_BYTES + 127) & ~127;
 constexpr int UNION_BYTES = WS_ALIGNED > WARPS * RING_BYTES ? WS_ALIGNED : WARPS * RING_BYTES;
 // union (rings | solve workspace), right-hand sides, barriers, misc
-constexpr int SMEM_BYTES = 128 /*alignment slack*/ + UNION_BYTES + WARPS * KP * 4 + (WARPS * NSTAGE + WARPS + 1) * 8 +
+constexpr int SMEM_BYTES = 128 /*alignment slack*/ + UNION_BYTES + WARPS * KP * 4 + (WARPS * NSTAGE + WARPS + 2) * 8 +
                            16 + 64 * 4;
 // instruction descriptor: D f32, A = B = tf32, both K-major, M = 64, N = 64
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
 // K-major, no swizzle: LBO (next core matrix along K: rows 4..7) = 128 B, SBO (next 8-feature group) = 272 B
 constexpr uint64_t DESC = (uint64_t(128 >> 4) << 16) | (uint64_t(GROUP_STRIDE >> 4) << 32) | (1ull << 46);
 }  // namespace tcx
-
-__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 
 // 4 consecutive features of a gathered row as f32
 __device__ __forceinline__ float4 load_quad(const float *other, int row, int fq)
@@ -95,7 +87,7 @@ __global__ void __launch_bounds__(tcx::NT, 3) als_tcx_kernel(lk_als_args a)
     uint64_t *stage_free = bars + warp * NSTAGE;
     uint64_t *acc_full = bars + WARPS * NSTAGE;
     uint64_t *solve_bar = acc_full + WARPS;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(solve_bar + 1);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(solve_bar + 2);  // solve_bar[1]: second pass of the updates
     int *s_misc = reinterpret_cast<int *>(s_tmem + 4);
 
     const ET *__restrict__ other = reinterpret_cast<const ET *>(a.d_other);
@@ -108,6 +100,7 @@ __global__ void __launch_bounds__(tcx::NT, 3) als_tcx_kernel(lk_als_args a)
     if (tid == 0) {
         for (int i = 0; i < WARPS * NSTAGE + WARPS; i++) mbar_init(&bars[i], 1);
         mbar_init(solve_bar, 4);
+        mbar_init(solve_bar + 1, 4);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -418,7 +411,7 @@ __global__ void __launch_bounds__(tcx::NT, 3) als_tcx_kernel(lk_als_args a)
                 const int c = 2 * p + hh;
                 if ((solve_mask >> c) & 1u) xold[p] = a.d_this[(size_t)s_misc[8 + 8 * c + 5] * k + gi];
             }
-            ctc::solve4<false, false>(tmem_base, yv, ws, solve_bar, solve_par, tid);
+            ctc::solve4<false, tcx::TCX_GJ>(tmem_base, yv, ws, solve_bar, solve_par, tid);
             __syncthreads();  // pivot flags
             float dpart[2] = {0.0f, 0.0f};
 #pragma unroll

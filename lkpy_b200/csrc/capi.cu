@@ -33,6 +33,7 @@ static const OptionDef OPTION_DEFS[] = {
     {"LK_ALS_TCS", &Options::als_tcs},
     {"LK_ALS_GJ", &Options::als_gj},
     {"LK_ALS_TF32", &Options::als_tf32},
+    {"LK_ALS_FLAGS", &Options::als_flags},
     {"LK_KNN_WARPS", &Options::knn_warps},
     {"LK_KNN_CTAS", &Options::knn_ctas},
     {"LK_KNN_SCORE_SEQ", &Options::knn_score_seq},

@@ -171,8 +171,8 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
 
 // Solve the four systems.  On entry the lower triangles of A are in TMEM (tmem_base = column 0 of
 // pair 0, lane field 0) and yv[p] holds the right-hand-side entry of this lane's row of system
-// 2p + (lane >> 4); on exit yv[p] holds the solution entry.  `bar` is an mbarrier (count 4: one commit per warp) used
-// only here, `par` its running phase parity.  ws.bad[s] is set when a pivot of system s was not
+// 2p + (lane >> 4); on exit yv[p] holds the solution entry.  `bar` points at two mbarriers (count 4 each: one commit per warp
+// and update pass) used only here, `par` is their running phase parity.  ws.bad[s] is set when a pivot of system s was not
 // positive (caller zeroes it).  All 128 threads must call.
 //
 // GJ = true turns the block elimination into a block Gauss-Jordan: at step j *every* other block
@@ -206,6 +206,15 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
     const int r = lane & 15, h = lane >> 4;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
     constexpr uint64_t DESC = SWAPPED_DESC ? DESC_KMAJOR_SWAPPED : DESC_KMAJOR;
+    // before step j rewrites the operand tiles: every trailing-update instruction of step j - 1 has completed
+    // (Cholesky variant: bar[1] collects the commits issued after the second pass, its phase parity follows
+    // bar[0]'s; the Gauss-Jordan variant commits everything to bar[0], which the next step has waited for)
+    auto wait_tiles_free = [&](const int j) {
+        if (!GJ && j > 0) {
+            while (!mbar_test(bar + 1, par ^ 1u)) {
+            }
+        }
+    };
 
 #pragma unroll 1
     for (int j = 0; j < 4; j++) {
@@ -260,6 +269,7 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
                 if (bad[p] && r == 0) ws.bad[s] = 1;
                 if constexpr (GJ) {
                     if (j < 3) {  // the pivot block row takes no part in this step's update
+                        if (p == 0) wait_tiles_free(j);
                         const int R = 16 * warp + r;
                         unsigned char *thi = ws.tiles + (s * 2) * TILE_BYTES + (R >> 3) * 512 + (R & 7) * 16;
 #pragma unroll
@@ -326,6 +336,7 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
                 }
             }
             mark3(6);
+            wait_tiles_free(j);
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 const int s = 2 * p + h;
@@ -397,16 +408,19 @@ __device__ __forceinline__ void solve4(const uint32_t tmem_base, float (&yv)[2],
                     umma_tf32(d + (uint32_t)(c - c0), a_lo, b_hi, idesc);
                 }
             };
-            if (GJ) {
+            if constexpr (GJ) {
+                // (look-ahead as below measured slower here: 3.64 vs 3.54 us*SM per system, tools/chol_tc_bench.cu)
                 update(c0, 64 - c0);
                 umma_commit(bar);
             } else {
                 // look-ahead: the 16 columns the next step works on (its diagonal block and triangular solves)
-                // first, and the barrier after them; the rest of the trailing update runs in their shadow (it
-                // is complete before the next step's commit: a commit covers everything its thread issued)
+                // first, and the barrier after them; the rest of the trailing update runs in their shadow and is
+                // committed to the second barrier, which the next step's writers of the operand tiles wait for
+                // (wait_tiles_free) — the tiles are read by these instructions until they complete
                 update(c0, 16);
                 umma_commit(bar);
                 if (c0 + 16 < 64) update(c0 + 16, 64 - c0 - 16);
+                umma_commit(bar + 1);
             }
         }
         __syncwarp();

@@ -74,8 +74,8 @@ __device__ __forceinline__ uint32_t blk_col(int p, int half, int jb) { return (u
 
 // Solve the two systems.  On entry the lower triangles are in TMEM (layout above, tmem_base = column 0,
 // lane field 0) and yv[p] holds the right-hand-side entry of this lane's row R of system p; on exit
-// yv[p] holds the solution entry.  `bar`: mbarrier with count NSYS (one commit per issuing warp),
-// `par` its running phase parity.  ws.bad[p] is set when a pivot of system p was not positive (caller
+// yv[p] holds the solution entry.  `bar`: two mbarriers with count NSYS (one commit per issuing warp and update
+// pass), `par` their running phase parity.  ws.bad[p] is set when a pivot of system p was not positive (caller
 // zeroes it).  All 128 threads must call.
 __device__ __forceinline__ void solve2(const uint32_t tmem_base, float (&yv)[NSYS], const Workspace &ws, uint64_t *bar,
                                        uint32_t &par, const int tid)
@@ -188,6 +188,12 @@ __device__ __forceinline__ void solve2(const uint32_t tmem_base, float (&yv)[NSY
                     }
                 }
             }
+            // the operand tiles are read by the previous step's trailing-update instructions until they complete:
+            // bar[1] collects the commits issued after their second pass (its phase parity follows bar[0]'s)
+            if (j > 0) {
+                while (!mbar_test(bar + 1, par ^ 1u)) {
+                }
+            }
 #pragma unroll
             for (int p = 0; p < NSYS; p++) {
                 float acc0 = 0.0f, acc1 = 0.0f;
@@ -248,7 +254,7 @@ __device__ __forceinline__ void solve2(const uint32_t tmem_base, float (&yv)[NSY
             const uint32_t boff_top = (uint32_t)(c0 >> 3) * 512;        // B = X rows c0.. of the top half
             const uint32_t boff_bot = bot + (uint32_t)(c0 >> 3) * 512;  // B = X rows 64 + c0..
             // look-ahead (as in chol_tc.cuh): the 16 columns the next step works on first, the barrier after
-            // them, the rest of the trailing update in their shadow (a later commit of this thread covers it)
+            // them, the rest of the trailing update in their shadow, committed to the second barrier
             auto update16 = [&](uint32_t d, uint32_t a_off, uint32_t b_off, int n, bool first) {
                 if (first)
                     update(d, a_off, b_off, n > 16 ? 16 : n);
@@ -272,6 +278,7 @@ __device__ __forceinline__ void solve2(const uint32_t tmem_base, float (&yv)[NSY
                 }
                 if (first) umma_commit(bar);
             }
+            umma_commit(bar + 1);  // second pass done: the tiles may be rewritten once this phase completes
         }
         __syncwarp();
         // only the warp that factors the next diagonal block needs the updated accumulators now

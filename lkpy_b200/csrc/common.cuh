@@ -41,8 +41,9 @@ struct Options {
     int als_tc_interleave = 1;  // 0: one accumulator per 64 TMEM columns (shared-memory solve only)
     int als_tc_occ = -1;        // cap on resident CTAs per SM of the tensor-core kernel
     int als_tcs = 1;            // 0: drain the systems to shared memory, one warp per solve
-    int als_gj = 0;             // 1: block Gauss-Jordan variant of the tensor-core solve
+    int als_gj = 1;             // 0: blocked Cholesky + block back substitution instead of block Gauss-Jordan (als_tc.cu)
     int als_tf32 = 1;           // 0: fp32 / non-uniformly weighted rows stay on the SIMT kernel
+    int als_flags = 1;          // als_tc_kernel: bit 0 streaming (L1 no-allocate) index loads
     int knn_warps = -1;         // warps per CTA of the kNN build (8, 16, 32)
     int knn_ctas = -1;          // resident CTAs per SM of the kNN build
     int knn_score_seq = 0;      // 1: sequential scoring kernel even with a contribution pool
@@ -50,6 +51,21 @@ struct Options {
 Options &options();
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// read-once global loads that do not allocate in L1 (streams that would otherwise evict the small tables
+// every CTA keeps re-reading)
+__device__ __forceinline__ int ld_stream_s32(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 
 // ---------------------------------------------------------------------------
 // PTX wrappers: mbarrier + bulk async copy (the TMA engine's 1-D path, SASS UBLKCP)

@@ -18,12 +18,12 @@ pytestmark = pytest.mark.gpu
 
 # solve variants of the tensor-core kernel (switches of lk_set_option, read by launch_als_tc / dispatch)
 VARIANTS = {
-    "tc-cholesky": {},  # default: blocked Cholesky with tcgen05 trailing updates (chol_tc.cuh)
-    "tc-gauss-jordan": {"LK_ALS_GJ": 1},  # block Gauss-Jordan variant of the same
+    "tc-gauss-jordan": {},  # default: block Gauss-Jordan in TMEM with tcgen05 trailing updates (chol_tc.cuh)
+    "tc-cholesky": {"LK_ALS_GJ": 0},  # blocked Cholesky + block back substitution variant of the same
     "smem-solve": {"LK_ALS_TCS": 0},  # systems drained to shared memory, one warp per solve
     "smem-solve-wide": {"LK_ALS_TCS": 0, "LK_ALS_TC_INTERLEAVE": 0},  # one accumulator per 64 columns
 }
-DEFAULTS = {"LK_ALS_TC": 1, "LK_ALS_TCS": 1, "LK_ALS_GJ": 0, "LK_ALS_TC_INTERLEAVE": 1}
+DEFAULTS = {"LK_ALS_TC": 1, "LK_ALS_TCS": 1, "LK_ALS_GJ": 1, "LK_ALS_TC_INTERLEAVE": 1}
 
 
 def _set(lk_options, variant):

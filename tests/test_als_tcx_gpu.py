@@ -1,6 +1,7 @@
 """
-GPU parity of als_tcx.cu — the tensor-core ALS kernel for fp32 gathered rows and non-uniform
-confidence weights (tf32 hi/lo split Gram, three MMAs per 8 rows) — against the f64 oracle with
+GPU parity of als_tcx.cu (k = 64) and of the tf32 gather path of als_tc128.cu (k = 128) — the tensor-core
+ALS kernels for fp32 gathered rows and non-uniform confidence weights (tf32 hi/lo split Gram, three MMAs
+per accumulator and 8 rows) — against the f64 oracle with
 UNROUNDED inputs (fp32 rows: the reference's own arithmetic, north-star tolerance 1e-4) and against
 the SIMT kernel on the same inputs.
 """
@@ -50,14 +51,14 @@ def _matrices(inter, kind, rng):
     return data.InteractionCSR.from_scipy(coo), data.InteractionCSR.from_scipy(coo.T)
 
 
+@pytest.mark.parametrize("k", [64, 128])
 @pytest.mark.parametrize("bf16", [False, True])
 @pytest.mark.parametrize("kind", ["implicit", "weighted", "explicit"])
-def test_tcx_parity(cuda_lib, lk_options, kind, bf16):
+def test_tcx_parity(cuda_lib, lk_options, kind, bf16, k):
     if kind == "implicit" and bf16:
-        pytest.skip("bf16 rows with uniform weights are als_tc.cu's configuration")
+        pytest.skip("bf16 rows with uniform weights are the kind::f16 configuration (als_tc.cu, als_tc128.cu)")
     inter = small_synth(900, 500, 40000, seed=21)
     rng = np.random.default_rng(21)
-    k = 64
     p = (rng.standard_normal((inter.n_users, k)) * 0.1).astype(np.float32)
     q = (rng.standard_normal((inter.n_items, k)) * 0.1).astype(np.float32)
     ui, iu = _matrices(inter, kind, rng)
@@ -77,13 +78,14 @@ def test_tcx_parity(cuda_lib, lk_options, kind, bf16):
         assert rel_fro(got, simt) < 6e-5, rel_fro(got, simt)
 
 
-def test_tcx_switch_off(cuda_lib, lk_options):
+@pytest.mark.parametrize("k", [64, 128])
+def test_tcx_switch_off(cuda_lib, lk_options, k):
     """LK_ALS_TF32=0 sends fp32 rows back to the SIMT kernel (same bits as LK_ALS_TC=0)."""
     inter = small_synth(300, 200, 9000, seed=6)
     ui, _ = data.als_implicit_matrices(inter, 40.0)
     rng = np.random.default_rng(6)
-    p = (rng.standard_normal((300, 64)) * 0.1).astype(np.float32)
-    q = (rng.standard_normal((200, 64)) * 0.1).astype(np.float32)
+    p = (rng.standard_normal((300, k)) * 0.1).astype(np.float32)
+    q = (rng.standard_normal((200, k)) * 0.1).astype(np.float32)
     lk_options("LK_ALS_TF32", 0)
     a, _, _ = _run("implicit", ui, p, q, 0.1)
     lk_options("LK_ALS_TF32", 1)
@@ -92,14 +94,15 @@ def test_tcx_switch_off(cuda_lib, lk_options):
     assert np.array_equal(a.view(np.int32), b.view(np.int32))
 
 
+@pytest.mark.parametrize("k", [64, 128])
 @pytest.mark.parametrize("kind", ["implicit", "weighted", "explicit"])
-def test_tcx_split_rows_deterministic(cuda_lib, lk_options, kind):
+def test_tcx_split_rows_deterministic(cuda_lib, lk_options, kind, k):
     inter = small_synth(300, 200, 20000, seed=5)
     rng = np.random.default_rng(5)
     _ui, iu = _matrices(inter, kind, rng)
     mode = "explicit" if kind == "explicit" else "implicit"
-    p = (rng.standard_normal((300, 64)) * 0.1).astype(np.float32)
-    q = (rng.standard_normal((200, 64)) * 0.1).astype(np.float32)
+    p = (rng.standard_normal((300, k)) * 0.1).astype(np.float32)
+    q = (rng.standard_normal((200, k)) * 0.1).astype(np.float32)
     a, _, plan = _run(mode, iu, q, p, 0.1, chunk_nnz=32)
     assert plan.n_split_rows > 0
     b, _, _ = _run(mode, iu, q, p, 0.1, chunk_nnz=32)
@@ -107,7 +110,10 @@ def test_tcx_split_rows_deterministic(cuda_lib, lk_options, kind):
     ref, _ = _oracle(mode, iu, q, p, 0.1)
     assert rel_fro(a, ref) < 1e-4
     c, _, _ = _run(mode, iu, q, p, 0.1, chunk_nnz=1 << 20)
-    assert rel_fro(a, c) < 1e-5
+    # split (32-nonzero parts added with round-to-nearest) vs unsplit (one round-toward-zero accumulation chain
+    # per row): the difference is the accumulator's truncation bias (1.4e-5 measured at k = 128 with uniform
+    # weights, more with sqrt(v)-scaled rows); both sit inside the 1e-4 tolerance against the oracle above
+    assert rel_fro(a, c) < (1e-5 if k == 64 else 1e-4)
 
 
 def test_tcx_badly_conditioned(cuda_lib, lk_options):

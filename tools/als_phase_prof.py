@@ -17,12 +17,12 @@ tr = ImplicitMFTrainer(sc, Dataset(inter), TrainingOptions(rng=42))
 for _ in range(3):
     tr.train_epoch_device()
 torch.cuda.synchronize()
-names = ["fetch", "gather+mma", "wait acc", "readout+fence", "split", "solve", "end sync", "-"]
+names = ["fetch", "gather+mma", "wait acc", "readout+fence", "split", "preload (+prefetch)", "end sync", "solve4", "write-back"]
 for label, plan, this, other, obf, reg in (
     ("user half", tr.u_plan, tr.d_users, tr.d_items, tr.d_items_bf16, 0.1),
     ("item half", tr.i_plan, tr.d_items, tr.d_users, tr.d_users_bf16, 0.1),
 ):
-    buf = torch.zeros(8, dtype=torch.int64, device=this.device)
+    buf = torch.zeros(16, dtype=torch.int64, device=this.device)
     engine.PROF_BUFFER = buf
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     otor = engine.als_otor(other, reg, tr.otor_ws, obf)
@@ -34,5 +34,5 @@ for label, plan, this, other, obf, reg in (
     c = buf.cpu().numpy().astype(np.float64)
     tot = c.sum()
     print(f"{label}: {e0.elapsed_time(e1):.3f} ms; chunks {plan.n_chunks}, split rows {plan.n_split_rows}")
-    for n, v in zip(names, c):
+    for n, v in zip(names, c[: len(names)]):
         print(f"   {n:14s} {v / tot * 100:5.1f}%   {v / max(plan.n_chunks / 4, 1):10.0f} cycles/group")

@@ -24,10 +24,11 @@ bench(const float *A, const float *y, float *x, int *badout, int n_groups, long 
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     ctc::Workspace ws = ctc::carve(base);
     uint64_t *bar = reinterpret_cast<uint64_t *>(base + ctc::WS_BYTES + 16);
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 1);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 2);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(bar, 4);
+        mbar_init(bar + 1, 4);
         mbar_fence_init();
     }
     if (warp == 0) {
