@@ -295,7 +295,8 @@ def _als_task(mode: int, matrix: Any, this: np.ndarray, other: np.ndarray, otor,
     def run_locked(task: AccelTask) -> float:
         dev = _lib.require_device()
         dm = _cached(matrix, "csr", lambda: engine.DeviceCSR.from_host(csr, dev))
-        chunk = engine.TF32_CHUNK_NNZ if k == 64 else engine.DEFAULT_CHUNK_NNZ  # host arrays are fp32 rows
+        # host arrays are fp32 rows: the tf32 tensor-core paths at k = 64 / 128
+        chunk = {64: engine.TF32_CHUNK_NNZ, 128: engine.TF32_CHUNK_NNZ_K128}.get(k, engine.DEFAULT_CHUNK_NNZ)
         plan = _cached(matrix, f"plan{k}", lambda: engine.ALSHalfPlan.create(dm, k, chunk))
         d_this = torch.from_numpy(this).to(dev)
         d_other = torch.from_numpy(other).to(dev)

@@ -268,10 +268,11 @@ class ALSTrainerBase(ModelTrainer):
     def _chunk_nnz(self, k: int) -> int:
         weighted = self.MODE == _lib.LK_ALS_IMPLICIT and getattr(self.config, "use_ratings", False)
         bf16_uniform = self.config.gather_dtype == "bfloat16" and not weighted
-        if (k == 64 and not bf16_uniform) or k == 128:
-            # shorter parts where a tensor-core accumulator would otherwise take hundreds of round-toward-zero
-            # additions (engine.TF32_CHUNK_NNZ): the tf32 paths make three per 8 rows, and at k = 128 the
-            # 100 M-interaction item rows reach 1e-4 on the bf16 path otherwise
+        # shorter parts where a tensor-core accumulator would otherwise take hundreds of round-toward-zero
+        # additions (engine.TF32_CHUNK_NNZ*): the tf32 paths make three per 8 rows, the bf16 path one per 16
+        if k == 128:
+            return engine.TF32_CHUNK_NNZ if bf16_uniform else engine.TF32_CHUNK_NNZ_K128
+        if k == 64 and not bf16_uniform:
             return engine.TF32_CHUNK_NNZ
         return engine.DEFAULT_CHUNK_NNZ
 

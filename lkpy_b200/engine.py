@@ -24,6 +24,10 @@ DEFAULT_CHUNK_NNZ = 4096
 #: round-toward-zero, three times per 8 gathered rows on that path, so the error of a partial Gram grows with
 #: its length (measured ~2.3e-8 relative per nonzero); parts are summed with round-to-nearest by the CUDA cores
 TF32_CHUNK_NNZ = 1024
+#: fp32 rows / per-nonzero weights at k = 128: the 128x128 solve amplifies the same Gram bias further — 1024-nonzero
+#: parts put the 100 M-interaction item rows at 2.0e-4 (8 GPUs, profiles/r02_als100m_n8.json), a quarter of that
+#: length keeps them inside the 1e-4 tolerance
+TF32_CHUNK_NNZ_K128 = 256
 #: engine limits the reference does not have: validated up front by the configs
 ALS_MAX_FEATURES = 128
 KNN_SCORE_MAX_NBRS = 128

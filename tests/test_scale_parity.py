@@ -52,6 +52,32 @@ def test_als_half_steps_at_ml25m_shape(cuda_lib, ml25m, gather):
         torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("gather", ["bf16", "fp32"])
+def test_als_item_half_step_k128_at_ml25m_shape(cuda_lib, ml25m, gather):
+    """features = 128 (BASELINE configs[3]'s width) on the long item rows of the ML-25M shape: the
+    three-accumulator Gram and the 128x128 in-TMEM solve of als_tc128.cu, kind::f16 (bf16 rows) and tf32 x3
+    (fp32 rows), parts as long as the trainers plan them (ALSTrainerBase._chunk_nnz)."""
+    dev = _lib.require_device()
+    k = 128
+    _ui, iu = data.als_implicit_matrices(ml25m, WEIGHT)
+    rng = np.random.default_rng(99)
+    p0 = (rng.standard_normal((ml25m.n_users, k)) * 0.1).astype(np.float32)
+    q0 = (rng.standard_normal((ml25m.n_items, k)) * 0.1).astype(np.float32)
+    chunk = engine.TF32_CHUNK_NNZ if gather == "bf16" else engine.TF32_CHUNK_NNZ_K128
+    plan = engine.ALSHalfPlan.create(engine.DeviceCSR.from_host(iu, dev), k, chunk)
+    assert plan.n_split_rows > 0
+    d_this, d_other = torch.from_numpy(q0).to(dev), torch.from_numpy(p0).to(dev)
+    obf = torch.empty_like(d_other, dtype=torch.bfloat16) if gather == "bf16" else None
+    otor = engine.als_otor(d_other, REG, engine.OtorWorkspace.create(k, dev), obf)
+    engine.als_half_epoch(plan, _lib.LK_ALS_IMPLICIT, d_this, obf if obf is not None else d_other, otor=otor)
+    torch.cuda.synchronize()
+    assert int(plan.status.item()) == 0
+    rows = parity.sample_als_rows(iu.indptr, k, chunk, n_random=300, seed=11, max_nnz=20_000, n_split=24)
+    got = d_this[torch.from_numpy(rows).to(dev)].cpu().numpy()
+    r = parity.check_als_half("implicit", iu, rows, q0[rows], p0, got, REG, gather == "bf16")
+    assert r["ok"] and r["rel_fro_vs_f64_oracle"] < 1e-4, r
+
+
 def test_knn_build_rows_at_ml25m_shape(cuda_lib, ml25m):
     dev = _lib.require_device()
     kui, kiu, _ = data.knn_item_matrices(ml25m, True)
