@@ -319,7 +319,7 @@ def make_data():
     from lkpy_b200 import data
 
     t0 = time.time()
-    inter = data.synth_interactions(**data.ML25M_SHAPE)
+    inter = data.synth_interactions_cached(os.environ.get("LK_BENCH_DATA_CACHE"), **data.ML25M_SHAPE)
     log(f"[bench] synthetic ML-25M-shaped data: {inter.n_users}x{inter.n_items}, nnz {inter.nnz} ({time.time() - t0:.1f}s)")
     return inter
 

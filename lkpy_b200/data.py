@@ -93,6 +93,26 @@ class Interactions:
         return sps.coo_array((v, (self.users, self.items)), shape=(self.n_users, self.n_items))
 
 
+def synth_interactions_cached(path: str | None, **shape) -> Interactions:
+    """``synth_interactions(**shape)`` through an optional ``.npz`` file: profiling scripts run the benchmark
+    several times on one box and the generator takes half a minute; the cached arrays are the generator's own
+    (same seed, same bits)."""
+    import os
+
+    if not path:
+        return synth_interactions(**shape)
+    key = np.array([shape["n_users"], shape["n_items"], shape["nnz"], shape.get("seed", 20260924)], dtype=np.int64)
+    if os.path.exists(path):
+        z = np.load(path)
+        if np.array_equal(z["key"], key):
+            return Interactions(z["users"], z["items"], z["ratings"], int(key[0]), int(key[1]))
+    inter = synth_interactions(**shape)
+    tmp = f"{path}.{os.getpid()}.tmp.npz"
+    np.savez(tmp, key=key, users=inter.users, items=inter.items, ratings=inter.ratings)
+    os.replace(tmp, path)
+    return inter
+
+
 def load_ml_small() -> Interactions:
     """Load the ml-latest-small fixture (see module docstring)."""
     f = GOLDEN_DIR / "ml_small.npz"

@@ -19,7 +19,9 @@ K, WEIGHT, REG = 64, 40.0, 0.1
 
 @pytest.fixture(scope="module")
 def ml25m():
-    return data.synth_interactions(**data.ML25M_SHAPE)
+    import os
+
+    return data.synth_interactions_cached(os.environ.get("LK_BENCH_DATA_CACHE"), **data.ML25M_SHAPE)
 
 
 @pytest.mark.parametrize("gather", ["bf16", "fp32"])

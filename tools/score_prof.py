@@ -11,7 +11,7 @@ from lkpy_b200 import _lib, data, engine, prep
 
 n_q = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 dev = _lib.require_device()
-inter = data.synth_interactions(**data.ML25M_SHAPE)
+inter = data.synth_interactions_cached(__import__("os").environ.get("LK_BENCH_DATA_CACHE"), **data.ML25M_SHAPE)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
 ui, iu, means = prep.knn_item_matrices_device(t(inter.users), t(inter.items), t(inter.ratings), inter.n_users, inter.n_items, True)
 plan = engine.KnnBuildPlan.create(ui, iu)
