@@ -839,6 +839,33 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
     cost = plan.cost.cpu().numpy()
     products = int(cost.sum()) - inter.nnz  # sim_row skips the diagonal entry of every (item, user) visit
 
+    def score_users(st, R, u_begin: int, u_end: int):
+        """Every user of [u_begin, u_end): the whole history against every item, in batches; device time (ms),
+        users scored, similarity entries touched, finite scores."""
+        B = max(1, min(args.score_batch, max(u_end - u_begin, 1)))
+        row_len = (st.sim_indptr[1:] - st.sim_indptr[:-1]).cpu().numpy()
+        a_lo, a_hi = int(R.indptr[u_begin]), int(R.indptr[u_end])
+        d_ri = torch.from_numpy(R.indices[a_lo:a_hi].astype(np.int32)).to(dev)
+        d_rv = torch.from_numpy((R.data[a_lo:a_hi] - means[R.indices[a_lo:a_hi]]).astype(np.float32)).to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total_ms, scored, touched, finite = 0.0, 0, 0, 0
+        for u0 in range(u_begin, u_end, B):
+            u1 = min(u0 + B, u_end)
+            a0, a1 = int(R.indptr[u0]) - a_lo, int(R.indptr[u1]) - a_lo
+            ref_ptr = torch.from_numpy((R.indptr[u0 : u1 + 1] - R.indptr[u0]).astype(np.int64)).to(dev)
+            if u0 == u_begin:  # warm-up launch
+                st.score_all_items(ref_ptr, d_ri[a0:a1], d_rv[a0:a1], KNN_MAX_NBRS, 1)
+            e0.record()
+            sc, ct = st.score_all_items(ref_ptr, d_ri[a0:a1], d_rv[a0:a1], KNN_MAX_NBRS, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            scored += u1 - u0
+            touched += int(row_len[R.indices[a_lo + a0 : a_lo + a1]].sum())
+            finite += int(torch.isfinite(sc).sum().item())
+            del sc, ct
+        return total_ms, scored, touched, finite
+
     def check_parity(indptr, cols, vals, extra: dict | None = None):
         if args.no_parity or rank != 0:
             return
@@ -891,14 +918,46 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             extra = {"result_equal_across_ranks": bool(torch.equal(lo, hi))}
+        # scoring shards by user: the similarity matrix is replicated after the build, every rank
+        # scores a contiguous user range balanced by history length; no collective on the data path
+        from lkpy_b200.parallel import row_bounds_by_nnz
+
+        dist.barrier()
+        local = torch.zeros(4, device=dev, dtype=torch.float64)  # ok, ms, users, finite scores
+        err = ""
+        try:  # no collective inside: a rank that fails here still reaches the reductions below
+            R = inter.coo().tocsr()
+            n_score = inter.n_users if args.score_users <= 0 else min(args.score_users, inter.n_users)
+            bounds = row_bounds_by_nnz(R.indptr[: n_score + 1], world)
+            st = engine.KnnScorerState.create(inter.n_items, *engine.topk_rows_to_csr(cols, vals, cnt), dev)
+            s_ms, scored, _touched, finite = score_users(st, R, int(bounds[rank]), int(bounds[rank + 1]))
+            local = torch.tensor([1.0, s_ms, float(scored), float(finite)], device=dev, dtype=torch.float64)
+            del st
+        except Exception as e:  # the scoring line must not take the build line (and the ALS headline) down with it
+            err = f"{type(e).__name__}: {e}"
+        mn, mx, sm = local.clone(), local.clone(), local.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        if float(mn[0].item()) == 1.0:
+            score = {
+                "users": int(sm[2].item()), "targets_per_user": inter.n_items, "ms": float(mx[1].item()),
+                "users_per_s": float(sm[2].item()) / (float(mx[1].item()) * 1e-3),
+                "scored_fraction": float(sm[3].item()) / max(float(sm[2].item()) * inter.n_items, 1.0),
+                "parallelism": f"users sharded by history length over {world} GPUs, similarity matrix replicated; "
+                               "time = max over ranks of the summed device time of the rank's launches",
+            }  # fmt: skip
+        else:
+            score = {"error": err or "a rank failed"}
         if rank != 0:
             return None
         check_parity(*engine.topk_rows_to_csr(cols, vals, cnt), extra=extra)
-        log(f"[bench] kNN build x{world}: {ms:.1f} ms = {inter.n_items / (ms * 1e-3):.0f} items/s")
+        log(f"[bench] kNN build x{world}: {ms:.1f} ms = {inter.n_items / (ms * 1e-3):.0f} items/s; score {score}")
         return {
             "workload": "ML-25M-shaped synthetic ItemKNNScorer explicit, min_sim=1e-6, save_nbrs=20 (BASELINE configs[2])",
             "build_ms": ms, "build_items_per_s": inter.n_items / (ms * 1e-3),
             "neighbours_kept": int(cnt.sum().item()), "parallelism": f"item rows dealt by cost over {world} GPUs",
+            "score": score,
         }  # fmt: skip
 
     def build():
@@ -999,27 +1058,7 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
     R = inter.coo().tocsr()
     n_score = inter.n_users if args.score_users <= 0 else min(args.score_users, inter.n_users)
     B = max(1, min(args.score_batch, n_score))
-    row_len = (indptr[1:] - indptr[:-1]).cpu().numpy()
-    d_ri = torch.from_numpy(R.indices.astype(np.int32)).to(dev)
-    d_rv = torch.from_numpy((R.data - means[R.indices]).astype(np.float32)).to(dev)
-    total_ms, scored, touched = 0.0, 0, 0
-    finite = 0
-    for u0 in range(0, n_score, B):
-        u1 = min(u0 + B, n_score)
-        nb = u1 - u0
-        a0, a1 = int(R.indptr[u0]), int(R.indptr[u1])
-        ref_ptr = torch.from_numpy((R.indptr[u0 : u1 + 1] - a0).astype(np.int64)).to(dev)
-        if u0 == 0:  # warm-up launch
-            st.score_all_items(ref_ptr, d_ri[a0:a1], d_rv[a0:a1], KNN_MAX_NBRS, 1)
-        e0.record()
-        sc, ct = st.score_all_items(ref_ptr, d_ri[a0:a1], d_rv[a0:a1], KNN_MAX_NBRS, 1)
-        e1.record()
-        torch.cuda.synchronize()
-        total_ms += e0.elapsed_time(e1)
-        scored += nb
-        touched += int(row_len[R.indices[a0:a1]].sum())
-        finite += int(torch.isfinite(sc).sum().item())
-        del sc, ct
+    total_ms, scored, touched, finite = score_users(st, R, 0, n_score)
     alg_s = knn_score_bytes(touched, int(R.indptr[n_score]), scored * inter.n_items)
     ach_s = alg_s / (total_ms * 1e-3) / 1e9
     out["score"] = {

@@ -68,7 +68,7 @@ LK_API int lk_device_info(int *sm_count, int *cc);
 /* Diagnostic switches (kernel variants kept for comparison; none changes results beyond rounding).
  * Each is also an environment variable of the same name, read once when the library first needs
  * it — never per launch; after that only lk_set_option changes it.  Names: LK_ALS_TC,
- * LK_ALS_TC_INTERLEAVE, LK_ALS_TC_OCC, LK_ALS_TCS, LK_ALS_GJ, LK_ALS_TF32, LK_KNN_WARPS,
+ * LK_ALS_TC_INTERLEAVE, LK_ALS_TC_OCC, LK_ALS_TCS, LK_ALS_GJ, LK_ALS_TF32, LK_ALS_FLAGS, LK_KNN_WARPS,
  * LK_KNN_CTAS, LK_KNN_SCORE_SEQ (meaning: lkpy_b200/csrc/common.cuh, struct Options). */
 LK_API int lk_set_option(const char *name, int value);
 LK_API int lk_get_option(const char *name, int *value);
