@@ -69,7 +69,7 @@ LK_API int lk_device_info(int *sm_count, int *cc);
  * Each is also an environment variable of the same name, read once when the library first needs
  * it — never per launch; after that only lk_set_option changes it.  Names: LK_ALS_TC,
  * LK_ALS_TC_INTERLEAVE, LK_ALS_TC_OCC, LK_ALS_TCS, LK_ALS_GJ, LK_ALS_TF32, LK_ALS_FLAGS, LK_KNN_WARPS,
- * LK_KNN_CTAS, LK_KNN_SCORE_SEQ (meaning: lkpy_b200/csrc/common.cuh, struct Options). */
+ * LK_KNN_CTAS, LK_KNN_SCORE_SEQ, LK_KNN_SCORE_CTAS (meaning: lkpy_b200/csrc/common.cuh, struct Options). */
 LK_API int lk_set_option(const char *name, int value);
 LK_API int lk_get_option(const char *name, int *value);
 
@@ -287,11 +287,14 @@ typedef struct lk_knn_score_args {
     int32_t user_mode;
     int32_t n_matrix_rows;       /* user mode: rows of the rating matrix (item mode: unused, = n_items) */
     /* Dense mode — d_tgt_indptr == NULL and d_tgt_items == NULL: every query is scored against ALL
-     * items in index order; d_scores / d_counts / d_acc_ws / d_acc_tw are [n_queries * n_items] (the two
-     * scratch arrays are only touched at targets that receive contributions), d_acc_cnt is not used, the
-     * contribution pool is required.  A CTA handles a query; d_slotmap provides one n_items row per CTA
-     * (slotmap_warps >= lk_knn_score_dense_ctas()) for the touched-target list of the heaviest queries. */
-    int32_t *d_deferred;         /* reserved (unused) */
+     * items in index order; d_scores / d_counts are [n_queries * n_items] and written exactly once, d_acc_cnt
+     * is not used, the contribution pool is required.  A CTA handles a query and keeps its state per CTA:
+     * d_slotmap provides one n_items row per CTA (slotmap_warps >= lk_knn_score_dense_ctas()) that must be
+     * all ZERO on entry and is left all zero (item -> touched-target number), d_acc_ws / d_acc_tw one
+     * n_items row per CTA each ([min(n_queries, lk_knn_score_dense_ctas()) * n_items] 32-bit words:
+     * list offsets / cursors by touched-target number). */
+    int32_t *d_deferred;         /* dense mode, optional: [n_queries] order in which the queries are handed to the CTAs
+                                  * (a permutation; longest histories first keeps the tail of the launch short) */
     int32_t *d_n_deferred;       /* reserved (unused) */
 } lk_knn_score_args;
 

@@ -37,6 +37,7 @@ static const OptionDef OPTION_DEFS[] = {
     {"LK_KNN_WARPS", &Options::knn_warps},
     {"LK_KNN_CTAS", &Options::knn_ctas},
     {"LK_KNN_SCORE_SEQ", &Options::knn_score_seq},
+    {"LK_KNN_SCORE_CTAS", &Options::knn_score_ctas},
 };
 
 Options &options()

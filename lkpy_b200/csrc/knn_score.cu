@@ -537,20 +537,26 @@ __global__ void __launch_bounds__(256) knn_score_lists_kernel(lk_knn_score_args 
 // "score every candidate" case, the one the build+score metric is quoted on).  The list kernel above
 // makes several passes over a query's whole target list — 59 k slots of which ~3 k ever receive a
 // contribution — and needs a per-warp slot map; here the target of a contribution IS its output
-// position, so a CTA per query
-//   1. streams the NaN / 0 fill of the query's output rows (the only O(n_items) work left, coalesced),
-//   2. flattens the contributions of a chunk of the history over its 256 threads (row extents in shared
-//      memory, block scan, one binary search per contribution) and counts them with atomics directly on
-//      the count row, collecting the targets touched for the first time (shared list, spilling into a
-//      per-CTA global list for the heaviest users),
-//   3. lays the touched targets' lists out in the contribution pool (block scan over the list),
-//   4. fills them with the same flattened walk, and
-//   5. gives every touched target to one thread: sort by history position, replay through the
-//      accumulator (vector sums in push order / BinaryHeap movement past max_nbrs) — the same bits as
-//      the sequential walk.
+// position.  A CTA per query; everything that is touched at random lives in a slot map of the CTA's own
+// (one int per item, reused for every query the CTA handles, so it stays in L2) and in compact
+// per-CTA arrays indexed by "touched target number"; the query's output rows are written exactly once:
+//   1. count: the contributions of a chunk of the history are flattened over the 256 threads (row extents
+//      in shared memory, block scan, one binary search per contribution) and counted with atomics on the
+//      slot map; a target touched for the first time joins the list of touched targets (shared memory,
+//      spilling into the query's own — still unwritten — count row);
+//   2. layout: block scan over the touched targets' counts gives every list its offset in the contribution
+//      pool; the slot map entry becomes the touched-target number;
+//   3. fill: the same flattened walk appends (history position, weight, value) to the lists;
+//   4. replay: one thread per touched target sorts its list by history position and runs it through the
+//      accumulator (vector sums in push order / BinaryHeap movement past max_nbrs) — the same bits as the
+//      sequential walk;
+//   5. one coalesced pass writes the score and count rows — the result where the slot map has an entry,
+//      NaN / 0 elsewhere — and clears the slot map for the next query.
+// (Round-2 v2 counted on the output row itself and kept [n_queries x n_items] offset / cursor rows: 2.1 MB
+// of DRAM traffic per ML-25M-shaped query, twice its output, L2 hit rate 28 %.)
 // ---------------------------------------------------------------------------------------------
 constexpr int DENSE_THREADS = 256;
-constexpr int DENSE_ACTIVE_CAP = 8192;  // touched targets kept in shared memory (the rest: d_slotmap row of the CTA)
+constexpr int DENSE_ACTIVE_CAP = 8192;  // touched targets kept in shared memory (the rest: the query's count row)
 constexpr int DENSE_HIST_CHUNK = 2048;  // history entries flattened at a time
 
 struct DenseSmem {
@@ -590,10 +596,11 @@ __global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_s
     const int limit = a.max_nbrs;
     const int64_t NI = a.n_items;
     PoolEnt *pool = reinterpret_cast<PoolEnt *>(a.d_pool);
-    int32_t *acc_off = reinterpret_cast<int32_t *>(a.d_acc_ws);  // [n_queries * n_items] scratch, touched targets only
-    int32_t *acc_cur = reinterpret_cast<int32_t *>(a.d_acc_tw);
-    int32_t *g_active = a.d_slotmap + (size_t)blockIdx.x * NI;  // overflow of the shared list
-    auto active_at = [&](int i) { return i < DENSE_ACTIVE_CAP ? sm.active[i] : g_active[i - DENSE_ACTIVE_CAP]; };
+    // per-CTA state, reused by every query this CTA handles
+    int32_t *slot = a.d_slotmap + (size_t)blockIdx.x * NI;  // all zero between queries
+    int32_t *offs = reinterpret_cast<int32_t *>(a.d_acc_ws) + (size_t)blockIdx.x * NI;  // [touched target] list offset, later score bits
+    int32_t *curs = reinterpret_cast<int32_t *>(a.d_acc_tw) + (size_t)blockIdx.x * NI;  // [touched target] list cursor, later count
+    constexpr int CU = 4;  // contributions per thread and step of the flattened walk
 
     for (;;) {
         if (tid == 0) {
@@ -601,21 +608,19 @@ __global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_s
             s_nactive = 0;
         }
         __syncthreads();
-        const int q = s_q;
-        if (q >= a.n_queries) break;
+        if (s_q >= a.n_queries) break;
+        const int q = a.d_deferred ? a.d_deferred[s_q] : s_q;  // optional hand-out order (heaviest queries first)
         const int64_t r0 = a.d_ref_indptr[q], r1 = a.d_ref_indptr[q + 1];
         float *scores = a.d_scores + (int64_t)q * NI;
         int32_t *counts = a.d_counts + (int64_t)q * NI;
-        int32_t *qoff = acc_off + (int64_t)q * NI, *qcur = acc_cur + (int64_t)q * NI;
+        // the query's count row is not written before step 5: until then it holds the tail of the touched list
+        auto active_at = [&](int i) { return i < DENSE_ACTIVE_CAP ? sm.active[i] : __ldcg(&counts[i - DENSE_ACTIVE_CAP]); };
 
-        // 1. fill: null score, zero neighbours
-        for (int64_t x = tid; x < NI; x += DENSE_THREADS) {
-            scores[x] = qnan;
-            counts[x] = 0;
-        }
-        __syncthreads();
-
-        // walk over the contributions of the query, flattened over the block: fn(history position, matrix entry, value)
+        // walk over the contributions of the query, flattened over the block:
+        // fn(lo, tcol, mval, pos0) gets four contributions per thread and step — lo[u] = history entry inside
+        // the chunk (-1: none), its matrix column and value, pos0 = history position of the chunk — with the
+        // matrix entries already loaded; the callers stage their own atomics the same way (all issued before
+        // any result is used): the walk is bound by memory latency, not by bandwidth
         auto for_each_contribution = [&](auto fn) {
             for (int64_t h0 = r0; h0 < r1; h0 += DENSE_HIST_CHUNK) {
                 const int nh = (int)min((int64_t)DENSE_HIST_CHUNK, r1 - h0);
@@ -640,43 +645,71 @@ __global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_s
                 if (tid == 0) sm.pre[nh] = s_carry;
                 __syncthreads();
                 const int total = sm.pre[nh];
-                for (int c = tid; c < total; c += DENSE_THREADS) {
-                    int lo = 0, hi = nh;  // last i with pre[i] <= c
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (sm.pre[mid] <= c) lo = mid; else hi = mid;
+                for (int c0 = tid; c0 < total; c0 += DENSE_THREADS * CU) {
+                    int lo[CU], tcol[CU];
+                    float mval[CU];
+#pragma unroll
+                    for (int u = 0; u < CU; u++) {
+                        const int c = c0 + u * DENSE_THREADS;
+                        lo[u] = -1;
+                        tcol[u] = 0;
+                        mval[u] = 0.0f;
+                        if (c < total) {
+                            int l = 0, hi = nh;  // last i with pre[i] <= c
+                            while (hi - l > 1) {
+                                const int mid = (l + hi) >> 1;
+                                if (sm.pre[mid] <= c) l = mid; else hi = mid;
+                            }
+                            lo[u] = l;
+                            const long long e = sm.row0[l] + (c - sm.pre[l]);
+                            tcol[u] = __ldg(a.d_sim_cols + e);
+                            if (a.d_sim_vals) mval[u] = __ldg(a.d_sim_vals + e);
+                        }
                     }
-                    fn((int)(h0 - r0) + lo, sm.row0[lo] + (c - sm.pre[lo]), sm.hv[lo]);
+                    fn(lo, tcol, mval, (int)(h0 - r0));
                 }
                 __syncthreads();
             }
         };
 
-        // 2. count
-        for_each_contribution([&](int, long long e, float hv) {
-            const int t = __ldg(a.d_sim_cols + e);
-            const float w = user_mode ? hv : __ldg(a.d_sim_vals + e);
-            if (w != w) atomicCAS(a.d_status, 0, 2);  // "similarity is null" (accum.rs:146-152)
-            if (atomicAdd(&counts[t], 1) == 0) {
-                const int idx = atomicAdd(&s_nactive, 1);
-                if (idx < DENSE_ACTIVE_CAP) sm.active[idx] = t; else g_active[idx - DENSE_ACTIVE_CAP] = t;
+        // 1. count
+        for_each_contribution([&](const int (&lo)[CU], const int (&tcol)[CU], const float (&mval)[CU], int) {
+            int old[CU];
+            bool null_w = false;
+#pragma unroll
+            for (int u = 0; u < CU; u++) {
+                old[u] = 1;
+                if (lo[u] >= 0) {
+                    const float w = user_mode ? sm.hv[lo[u]] : mval[u];
+                    null_w |= w != w;
+                    old[u] = atomicAdd(&slot[tcol[u]], 1);
+                }
+            }
+            if (null_w) atomicCAS(a.d_status, 0, 2);  // "similarity is null" (accum.rs:146-152)
+#pragma unroll
+            for (int u = 0; u < CU; u++) {
+                if (old[u] == 0) {  // first touch of this target
+                    const int idx = atomicAdd(&s_nactive, 1);
+                    if (idx < DENSE_ACTIVE_CAP) sm.active[idx] = tcol[u]; else __stcg(&counts[idx - DENSE_ACTIVE_CAP], tcol[u]);
+                }
             }
         });
         __threadfence_block();
         __syncthreads();
         const int n_active = s_nactive;
 
-        // 3. lay out the lists: block-wide exclusive scan of the touched targets' counts
+        // 2. lay out the lists: block-wide exclusive scan of the touched targets' counts; slot -> touched-target number
         if (tid == 0) s_carry = 0;
         __syncthreads();
         for (int i0 = 0; i0 < n_active; i0 += DENSE_THREADS) {
             const int i = i0 + tid;
             const int t = i < n_active ? active_at(i) : 0;
-            const int c = i < n_active ? __ldcg(&counts[t]) : 0;
+            const int c = i < n_active ? __ldcg(&slot[t]) : 0;
             const int off = block_excl_scan(c, s_scan, &s_carry, tid, lane, warp);
             if (i < n_active) {
-                qoff[t] = off;
-                qcur[t] = 0;
+                __stcg(&offs[i], off);
+                __stcg(&curs[i], 0);
+                __stcg(&slot[t], i + 1);
             }
         }
         const int total = s_carry;
@@ -686,30 +719,56 @@ __global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_s
         const unsigned long long base = s_base;
         if (base + (unsigned long long)total > (unsigned long long)a.pool_entries) {
             if (tid == 0) atomicCAS(a.d_status, 0, 3);  // pool too small (caller sizing error)
+            for (int i = tid; i < n_active; i += DENSE_THREADS) __stcg(&slot[active_at(i)], 0);  // leave the map clean
             __syncthreads();
             continue;
         }
 
-        // 4. fill the lists (arrival order; sorted per target below)
-        for_each_contribution([&](int pos, long long e, float hv) {
-            const int t = __ldg(a.d_sim_cols + e);
-            const float mv = a.d_sim_vals ? __ldg(a.d_sim_vals + e) : 0.0f;
-            const int kpos = atomicAdd(&qcur[t], 1);
-            PoolEnt ent;
-            ent.pos = pos;
-            ent.sim = user_mode ? hv : mv;
-            ent.rv = user_mode ? mv : hv;
-            ent.pad = 0;
-            pool[base + (unsigned long long)(__ldcg(&qoff[t]) + kpos)] = ent;
+        // 3. fill the lists (arrival order; sorted per target below)
+        for_each_contribution([&](const int (&lo)[CU], const int (&tcol)[CU], const float (&mval)[CU], int pos0) {
+            int ti[CU], kpos[CU], off[CU];
+#pragma unroll
+            for (int u = 0; u < CU; u++) ti[u] = lo[u] >= 0 ? __ldcg(&slot[tcol[u]]) - 1 : -1;
+#pragma unroll
+            for (int u = 0; u < CU; u++) {
+                kpos[u] = 0, off[u] = 0;
+                if (ti[u] >= 0) {
+                    kpos[u] = atomicAdd(&curs[ti[u]], 1);
+                    off[u] = __ldcg(&offs[ti[u]]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CU; u++) {
+                if (ti[u] >= 0) {
+                    const float hv = sm.hv[lo[u]];
+                    PoolEnt ent;
+                    ent.pos = pos0 + lo[u];
+                    ent.sim = user_mode ? hv : mval[u];
+                    ent.rv = user_mode ? mval[u] : hv;
+                    ent.pad = 0;
+                    pool[base + (unsigned long long)(off[u] + kpos[u])] = ent;
+                }
+            }
         });
         __threadfence_block();
         __syncthreads();
 
-        // 5. one thread per touched target: history order, then the accumulator
-        for (int i = tid; i < n_active; i += DENSE_THREADS) {
-            const int t = active_at(i);
-            const int n = __ldcg(&counts[t]);
-            PoolEnt *L = pool + base + (unsigned long long)__ldcg(&qoff[t]);
+        // 4. one thread per touched target: history order, then the accumulator
+        constexpr int RU = 4;
+        for (int i0 = tid; i0 < n_active; i0 += DENSE_THREADS * RU) {
+          int nn[RU], oo[RU];
+#pragma unroll
+          for (int v = 0; v < RU; v++) {
+              const int i = i0 + v * DENSE_THREADS;
+              nn[v] = i < n_active ? __ldcg(&curs[i]) : 0;
+              oo[v] = i < n_active ? __ldcg(&offs[i]) : 0;
+          }
+#pragma unroll 1
+          for (int v = 0; v < RU; v++) {
+            const int i = i0 + v * DENSE_THREADS;
+            if (i >= n_active) break;
+            const int n = nn[v];
+            PoolEnt *L = pool + base + (unsigned long long)oo[v];
             for (int u = 1; u < n; u++) {  // insertion sort by history position
                 const PoolEnt key = L[u];
                 int j = u - 1;
@@ -738,8 +797,36 @@ __global__ void __launch_bounds__(DENSE_THREADS) knn_score_dense_kernel(lk_knn_s
                 for (int u = 0; u < len; u++) ws = __fadd_rn(ws, __fmul_rn(d[u].w, d[u].v));
                 c = len;
             }
-            counts[t] = c;
-            if (c >= a.min_nbrs) scores[t] = explicit_fb ? ws / tw : tw;
+            __stcg(&curs[i], c);
+            __stcg(&offs[i], __float_as_int(c >= a.min_nbrs ? (explicit_fb ? ws / tw : tw) : qnan));
+          }
+        }
+        __threadfence_block();
+        __syncthreads();
+
+        // 5. the output rows, once, coalesced; the slot map goes back to zero
+        constexpr int FU = 8;
+        for (int64_t x0 = tid; x0 < NI; x0 += DENSE_THREADS * FU) {
+            int sl[FU];
+#pragma unroll
+            for (int u = 0; u < FU; u++) {
+                const int64_t x = x0 + u * DENSE_THREADS;
+                sl[u] = x < NI ? __ldcg(&slot[x]) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < FU; u++) {
+                const int64_t x = x0 + u * DENSE_THREADS;
+                if (x >= NI) break;
+                float sc = qnan;
+                int ct = 0;
+                if (sl[u] != 0) {
+                    sc = __int_as_float(__ldcg(&offs[sl[u] - 1]));
+                    ct = __ldcg(&curs[sl[u] - 1]);
+                    __stcg(&slot[x], 0);
+                }
+                __stcs(&scores[x], sc);
+                __stcs(&counts[x], ct);
+            }
         }
         __syncthreads();
     }
@@ -784,7 +871,12 @@ int lk_knn_score_batch(const lk_knn_score_args *args, void *stream)
         LK_REQUIRE(reinterpret_cast<uintptr_t>(a.d_pool) % 16 == 0 && a.pool_entries >= 0, LK_ERR_INVALID,
                    "lk_knn_score_batch: bad contribution pool");
         LK_CUDA_TRY(cudaMemsetAsync(a.d_pool_cursor, 0, sizeof(unsigned long long), st));
-        const int grid = (int)std::min<int64_t>(a.n_queries, lk_knn_score_dense_ctas());
+        // the per-CTA slot maps (n_items ints each) should stay in L2 next to the similarity matrix: two CTAs
+        // per SM instead of three when three rows per SM would take more than half of it
+        const Options &opt = options();
+        int per_sm = ((int64_t)sm_count() * 3 * a.n_items * 4 > (int64_t)(64 << 20)) ? 2 : 3;
+        if (opt.knn_score_ctas > 0) per_sm = std::min(3, opt.knn_score_ctas);
+        const int grid = (int)std::min<int64_t>(a.n_queries, (int64_t)sm_count() * per_sm);
         const int smem = (int)sizeof(DenseSmem);
         LK_CUDA_TRY(cudaFuncSetAttribute(knn_score_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         knn_score_dense_kernel<<<grid, DENSE_THREADS, smem, st>>>(a);

@@ -23,10 +23,15 @@ a1 = int(R.indptr[n_q])
 ref_ptr = t(R.indptr[: n_q + 1].astype(np.int64))
 ri = t(R.indices[:a1].astype(np.int32))
 rv = t((R.data[:a1] - means.cpu().numpy()[R.indices[:a1]]).astype(np.float32))
-for rep in range(2):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    sc, ct = st.score_all_items(ref_ptr, ri, rv, 20, 1)
-    e1.record()
-    torch.cuda.synchronize()
-    print(f"score_all_items {n_q} users: {e0.elapsed_time(e1):.2f} ms, scored fraction {torch.isfinite(sc).float().mean().item():.4f}", flush=True)
+for ctas in ([int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [-1]):
+    _lib.set_option("LK_KNN_SCORE_CTAS", abs(ctas) if ctas != -1 else -1)
+    engine.KnnScorerState.DENSE_LPT = ctas >= -1  # a negative count other than -1: index order instead of longest-first
+    for rep in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sc, ct = st.score_all_items(ref_ptr, ri, rv, 20, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"score_all_items {n_q} users, CTAs/SM option {ctas}: {e0.elapsed_time(e1):.2f} ms, scored fraction "
+              f"{torch.isfinite(sc).float().mean().item():.4f}", flush=True)
+        del sc, ct
