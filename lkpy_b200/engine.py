@@ -467,7 +467,10 @@ class KnnScorerState:
     n_rows: int = 0
     HEAP_TARGETS_PER_WARP = 2048
     USE_LISTS = True  # list-based kernel (parallel over the history); False: the sequential kernel
-    DENSE_LPT = False  # dense kernel: hand the queries out longest history first (measured slightly slower: 3.0 vs 2.7 ms per 4,096 ML-25M-shaped users)
+    #: dense kernel: hand the queries out longest history first when the batch is large enough for the heaviest
+    #: query (2.6 ms on its own at ML-25M shape: one thread sorts a popular target's list) to hide under the
+    #: rest; at 4,096 users per launch the launch is that query either way (measured 3.0 vs 2.7 ms)
+    DENSE_LPT_MIN_QUERIES = 8192
 
     def kernel_name(self) -> str:
         lists = self.USE_LISTS and _lib.get_option("LK_KNN_SCORE_SEQ") != 1
@@ -587,7 +590,7 @@ class KnnScorerState:
             a.d_pool, a.pool_entries, a.d_pool_cursor = ptr(pool), pool.numel() // 4, ptr(cursor)
             a.d_slotmap, a.slotmap_warps = ptr(spill), ctas  # per-CTA slot maps (all zero between launches)
             order = None
-            if self.DENSE_LPT and nq > 1:
+            if nq >= self.DENSE_LPT_MIN_QUERIES:
                 # longest histories first: a query costs what its history contributes, and the launch ends with
                 # its last query
                 order = torch.argsort(ref_indptr[1:] - ref_indptr[:-1], descending=True).to(torch.int32)
