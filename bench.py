@@ -1060,18 +1060,32 @@ def bench_knn(args, inter, dev, peak, peak_src, rank: int, world: int, parity: d
     R = inter.coo().tocsr()
     n_score = inter.n_users if args.score_users <= 0 else min(args.score_users, inter.n_users)
     B = max(1, min(args.score_batch, n_score))
-    total_ms, scored, touched, finite = score_users(st, R, 0, n_score)
-    alg_s = knn_score_bytes(touched, int(R.indptr[n_score]), scored * inter.n_items)
-    ach_s = alg_s / (total_ms * 1e-3) / 1e9
-    out["score"] = {
-        "users": scored, "targets_per_user": inter.n_items, "batch": B, "ms": total_ms,
-        "users_per_s": scored / (total_ms * 1e-3), "scored_fraction": finite / max(scored * inter.n_items, 1),
-        "roofline": {"bound": "hbm", "kernel": "knn_score_dense_kernel", "achieved": ach_s, "peak": peak, "unit": "GB/s",
-                     "frac": ach_s / peak, "traffic": None, "algorithmic_bytes": alg_s, "peak_source": peak_src},
-    }  # fmt: skip
-    out["build_plus_score_s"] = ms * 1e-3 + total_ms * 1e-3 * (inter.n_users / max(scored, 1))
-    log(f"[bench] kNN score: {scored} users x all items in {total_ms:.1f} ms = {out['score']['users_per_s']:.0f} users/s, "
-        f"{ach_s:.0f} GB/s algorithmic = {ach_s / peak:.3f} of peak")
+    try:
+        try:
+            total_ms, scored, touched, finite = score_users(st, R, 0, n_score)
+        except (torch.OutOfMemoryError, RuntimeError) as e:
+            # the wide default batch is a throughput choice, not a requirement: fall back to the batch the round's
+            # measurements were taken with rather than lose the line
+            log(f"[bench] kNN score at {B} users per launch failed ({type(e).__name__}: {e}); retrying at 4096")
+            torch.cuda.empty_cache()
+            args.score_batch = B = min(4096, n_score)
+            total_ms, scored, touched, finite = score_users(st, R, 0, n_score)
+        alg_s = knn_score_bytes(touched, int(R.indptr[n_score]), scored * inter.n_items)
+        ach_s = alg_s / (total_ms * 1e-3) / 1e9
+        out["score"] = {
+            "users": scored, "targets_per_user": inter.n_items, "batch": B, "ms": total_ms,
+            "users_per_s": scored / (total_ms * 1e-3), "scored_fraction": finite / max(scored * inter.n_items, 1),
+            "roofline": {"bound": "hbm", "kernel": "knn_score_dense_kernel", "achieved": ach_s, "peak": peak, "unit": "GB/s",
+                         "frac": ach_s / peak, "traffic": ncu_traffic("knn_score_dense_kernel_v3_bytes_per_2048_users", world),
+                         "traffic_note": "per launch of 2,048 users (the ncu capture), not per launch of this run",
+                         "algorithmic_bytes": alg_s, "peak_source": peak_src},
+        }  # fmt: skip
+        out["build_plus_score_s"] = ms * 1e-3 + total_ms * 1e-3 * (inter.n_users / max(scored, 1))
+        log(f"[bench] kNN score: {scored} users x all items in {total_ms:.1f} ms = {out['score']['users_per_s']:.0f} users/s, "
+            f"{ach_s:.0f} GB/s algorithmic = {ach_s / peak:.3f} of peak")
+    except Exception as e:  # the scoring line must not take the build line (and the ALS headline) down with it
+        out["score"] = {"error": f"{type(e).__name__}: {e}"}
+        log(f"[bench] kNN score failed: {out['score']['error']}")
     return out
 
 
