@@ -167,3 +167,45 @@ def test_arrow_csr_ingest_and_chunks():
     assert np.array_equal(sl.indices, cols[indptr[10] : indptr[30]])
     only = accel.as_host_csr(pa.ListArray.from_arrays(pa.array(indptr.astype(np.int32)), pa.array(cols)), 40)
     assert np.all(only.values == 1.0) and np.array_equal(only.indices, cols)
+
+
+def test_row_part_length_by_kernel_path():
+    """ALSTrainerBase._chunk_nnz: which row-part length each kernel path is planned with (the
+    tensor-core accumulators add with round-toward-zero, so the tf32 paths and k = 128 get shorter parts)."""
+    from types import SimpleNamespace
+
+    from lkpy_b200 import _lib, engine
+    from lkpy_b200.als import ALSTrainerBase
+
+    def chunk(k, gather, mode=_lib.LK_ALS_IMPLICIT, use_ratings=False):
+        me = SimpleNamespace(MODE=mode, config=SimpleNamespace(gather_dtype=gather, use_ratings=use_ratings))
+        return ALSTrainerBase._chunk_nnz(me, k)
+
+    assert chunk(64, "bfloat16") == engine.DEFAULT_CHUNK_NNZ  # als_tc_kernel: one accumulation per 16 rows
+    assert chunk(64, "float32") == engine.TF32_CHUNK_NNZ  # als_tcx_kernel
+    assert chunk(64, "bfloat16", use_ratings=True) == engine.TF32_CHUNK_NNZ  # weighted: tf32 path as well
+    assert chunk(64, "float32", mode=_lib.LK_ALS_EXPLICIT) == engine.TF32_CHUNK_NNZ
+    assert chunk(128, "bfloat16") == engine.TF32_CHUNK_NNZ  # als_tc128_kernel, kind::f16
+    assert chunk(128, "float32") == engine.TF32_CHUNK_NNZ_K128  # als_tc128_kernel, tf32 x3
+    assert chunk(128, "bfloat16", use_ratings=True) == engine.TF32_CHUNK_NNZ_K128
+    assert chunk(32, "float32") == engine.DEFAULT_CHUNK_NNZ  # SIMT kernel
+    assert engine.TF32_CHUNK_NNZ_K128 < engine.TF32_CHUNK_NNZ < engine.DEFAULT_CHUNK_NNZ
+
+
+def test_synthetic_matrix_cache_round_trip(tmp_path):
+    """data.synth_interactions_cached: the cached arrays are the generator's own, and a cache of another shape is
+    not reused."""
+    from lkpy_b200 import data
+
+    shape = dict(n_users=400, n_items=150, nnz=6000)
+    f = str(tmp_path / "cache.npz")
+    a = data.synth_interactions_cached(f, **shape)
+    b = data.synth_interactions_cached(f, **shape)  # from the file
+    c = data.synth_interactions(**shape)
+    for x in (a, b):
+        assert (x.n_users, x.n_items) == (c.n_users, c.n_items)
+        assert np.array_equal(x.users, c.users) and np.array_equal(x.items, c.items)
+        assert np.array_equal(x.ratings.view(np.int32), c.ratings.view(np.int32))
+    other = data.synth_interactions_cached(f, n_users=300, n_items=150, nnz=5000)
+    assert other.n_users == 300 and other.nnz == 5000
+    assert data.synth_interactions_cached(None, **shape).nnz == c.nnz
