@@ -107,3 +107,45 @@ def _worker(rank: int, world: int, port: int):
 
 def test_sharded_paths_world2():
     mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _worker_checks(rank: int, world: int, port: int):
+    """The cross-rank checks of the scale-out bench (bench_scale.py) on CPU tensors under gloo."""
+    import sys
+    from pathlib import Path
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+        import bench_scale
+
+        dev = torch.device("cpu")
+        g = torch.Generator().manual_seed(5)
+        u = torch.randint(0, 1000, (5000,), generator=g, dtype=torch.int32)
+        i = torch.randint(0, 300, (5000,), generator=g, dtype=torch.int32)
+        r = torch.rand(5000, generator=g)
+        # every rank holds the same matrix / the same result: both checks pass
+        assert bench_scale._inputs_equal_across_ranks([u, i, r], dev, world)
+        assert bench_scale._equal_across_ranks([u.float(), r], dev, world)
+        # one rating differs in its last bit on one rank (what a non-reproducible device prefix sum did to the
+        # generator): both checks must see it
+        r2 = r.clone()
+        if rank == 1:
+            r2.view(torch.int32)[1234] ^= 1
+        assert not bench_scale._inputs_equal_across_ranks([u, i, r2], dev, world)
+        assert not bench_scale._equal_across_ranks([r2], dev, world)
+        # user-sharded scoring: contiguous user ranges balanced by history length cover every user once
+        hist = np.concatenate([[0], np.cumsum(np.random.default_rng(3).integers(0, 400, 3000))])
+        b = row_bounds_by_nnz(hist, world)
+        mine = torch.zeros(3000, dtype=torch.int32)
+        mine[int(b[rank]) : int(b[rank + 1])] = 1
+        dist.all_reduce(mine)
+        assert bool((mine == 1).all())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cross_rank_checks_world2():
+    mp.spawn(_worker_checks, args=(2, _free_port()), nprocs=2, join=True)
