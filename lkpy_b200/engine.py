@@ -467,10 +467,10 @@ class KnnScorerState:
     n_rows: int = 0
     HEAP_TARGETS_PER_WARP = 2048
     USE_LISTS = True  # list-based kernel (parallel over the history); False: the sequential kernel
-    #: dense kernel: hand the queries out longest history first when the batch is large enough for the heaviest
-    #: query (2.6 ms on its own at ML-25M shape: one thread sorts a popular target's list) to hide under the
-    #: rest; at 4,096 users per launch the launch is that query either way (measured 3.0 vs 2.7 ms)
-    DENSE_LPT_MIN_QUERIES = 8192
+    #: dense kernel: batches of at least this many queries are handed out longest history first.  Off by default:
+    #: measured 3.0 vs 2.7 ms per 4,096 ML-25M-shaped users (the heaviest queries, started together, contend for
+    #: L2), and a random position costs a wide batch less than that (tools/score_prof.py toggles it)
+    DENSE_LPT_MIN_QUERIES = 1 << 30
 
     def kernel_name(self) -> str:
         lists = self.USE_LISTS and _lib.get_option("LK_KNN_SCORE_SEQ") != 1
