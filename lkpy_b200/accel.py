@@ -211,15 +211,59 @@ def as_host_csr(m: Any, n_cols: int | None = None) -> InteractionCSR:
     raise TypeError(f"cannot interpret {type(m).__name__} as a CSR matrix")  # csr.rs:160-195
 
 
+SPARSE_IDX_EXT_NAME = "lenskit.sparse_index"  # data/matrix.py:35
+_own_index_type: Any = None
+
+
+def sparse_index_type(dimension: int):
+    """
+    The Arrow type of the ``index`` field of a sparse row: int32 storage under the reference's
+    ``lenskit.sparse_index`` extension type, whose metadata carries the row dimension
+    (``SparseIndexType``, data/matrix.py:104-146; the Rust consumer attaches it at
+    sparse/consumer.rs:109).  ``SparseRowArray.from_array`` (knn/item.py:177) refuses a result whose index
+    field is a plain int32.  Inside a process that has imported lenskit the reference's own class is used
+    (it is the one its ``isinstance`` checks look for); otherwise a class with the same extension name and
+    serialisation — left unregistered, so that a later ``import lenskit`` can still register its own.
+    """
+    import sys
+
+    import pyarrow as pa
+
+    ref = getattr(sys.modules.get("lenskit.data.matrix"), "SparseIndexType", None)
+    if ref is not None:
+        return ref(int(dimension))
+    global _own_index_type
+    if _own_index_type is None:
+        import json
+
+        class SparseIndexType(pa.ExtensionType):
+            def __init__(self, dimension: int):
+                self.dimension = int(dimension)
+                super().__init__(pa.int32(), SPARSE_IDX_EXT_NAME)
+
+            def __arrow_ext_serialize__(self) -> bytes:
+                return json.dumps({"dimension": self.dimension}).encode()
+
+            @classmethod
+            def __arrow_ext_deserialize__(cls, storage_type, serialized):
+                return cls(json.loads(serialized.decode())["dimension"])
+
+        _own_index_type = SparseIndexType
+    return _own_index_type(int(dimension))
+
+
 def csr_to_arrow_chunks(csr: InteractionCSR, rows_per_chunk: int | None = None) -> list:
     """
     The result layout of ``compute_similarities`` (``ArrowCSRConsumer``, src/accel/sparse/consumer.rs:96-142):
-    a list of ``LargeListArray<Struct{index: int32, value: float32}>`` chunks in row order, which the
-    caller concatenates (``pa.chunked_array(...).combine_chunks()``, knn/item.py:173-177).  The struct
-    children view the CSR's own buffers; a chunk re-bases its offsets.
+    a list of ``LargeListArray<Struct{index: sparse_index(n_cols) over int32, value: float32}>`` chunks in row
+    order, which the caller concatenates and wraps (``pa.chunked_array(...).combine_chunks()`` then
+    ``SparseRowArray.from_array``, knn/item.py:173-177).  The struct children view the CSR's own buffers; a
+    chunk re-bases its offsets.
     """
     import pyarrow as pa
 
+    idx_type = sparse_index_type(csr.shape[1])
+    fields = [pa.field("index", idx_type), pa.field("value", pa.float32())]
     n = csr.shape[0]
     step = n if not rows_per_chunk else max(1, int(rows_per_chunk))
     indptr = np.asarray(csr.indptr, dtype=np.int64)
@@ -228,8 +272,11 @@ def csr_to_arrow_chunks(csr: InteractionCSR, rows_per_chunk: int | None = None) 
         hi = min(n, lo + step)
         a, b = int(indptr[lo]), int(indptr[hi])
         elems = pa.StructArray.from_arrays(
-            [pa.array(csr.indices[a:b], type=pa.int32()), pa.array(csr.values[a:b], type=pa.float32())],
-            names=["index", "value"],
+            [
+                pa.ExtensionArray.from_storage(idx_type, pa.array(csr.indices[a:b], type=pa.int32())),
+                pa.array(csr.values[a:b], type=pa.float32()),
+            ],
+            fields=fields,
         )
         out.append(pa.LargeListArray.from_arrays(pa.array(indptr[lo : hi + 1] - a, type=pa.int64()), elems))
         if hi >= n:

@@ -1,0 +1,187 @@
+"""
+Test harness: the reference's OWN Python classes for the hot path — ``lenskit.training``,
+``lenskit.pipeline.components.Component``, ``lenskit.data.matrix.SparseRowArray``,
+``lenskit.als._common / _implicit``, ``lenskit.knn.item`` — loaded from ``/root/reference`` file
+by file, with ``lenskit._accel`` bound to ``lkpy_b200.accel`` exactly as INTEGRATION.md §1 describes.
+
+The reference package cannot be imported as a whole here (its ``__init__`` needs ``lazy_loader`` /
+``structlog``, its data layer needs the Rust extension's ``IDIndex`` / ``CoordinateTable``), so the modules
+the hot path does not touch are replaced by small fakes: logging, the parallel helpers, and the slice of
+``lenskit.data`` the two trainers read (``Dataset.interactions().matrix().scipy(...)``, the vocabularies).
+Everything between the user's ``scorer.train(dataset)`` and the accelerator call is the reference's code.
+
+Build-container only: ``/root/reference`` does not exist on the GPU box (the tests that use this skip there).
+"""
+
+from __future__ import annotations
+
+import contextlib
+import importlib.util
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+from scipy.sparse import coo_array
+
+REF_SRC = Path("/root/reference/src/lenskit")
+
+
+def available() -> bool:
+    return (REF_SRC / "als" / "_implicit.py").exists()
+
+
+# ---------------------------------------------------------------------------
+# fakes for what the hot path does not touch
+# ---------------------------------------------------------------------------
+
+
+class _Log:
+    """structlog-shaped no-op logger."""
+
+    def bind(self, **_kw):
+        return self
+
+    def _noop(self, *_a, **_kw):
+        return None
+
+    debug = info = warning = warn = error = trace = _noop
+
+
+class _Stopwatch:
+    def __str__(self):
+        return "0s"
+
+
+class _Progress:
+    def __init__(self, *_a, **_kw):
+        self.updates = 0
+
+    def update(self, *_a, **_kw):
+        self.updates += 1
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *_a):
+        return False
+
+
+class _MatrixView:
+    """``data.interactions().matrix()``: the one call the trainers make on it."""
+
+    def __init__(self, inter):
+        self._inter = inter
+
+    def scipy(self, attribute: str | None = None, layout: str = "csr", **_kw):
+        it = self._inter
+        vals = it.ratings.astype(np.float32) if attribute == "rating" else np.ones(it.nnz, dtype=np.float32)
+        m = coo_array((vals, (it.users, it.items)), shape=(it.n_users, it.n_items))
+        return m if layout == "coo" else m.tocsr()
+
+
+class _Relationship:
+    def __init__(self, inter):
+        self._inter = inter
+
+    def matrix(self, **_kw):
+        return _MatrixView(self._inter)
+
+
+class FakeDataset:
+    """The slice of ``lenskit.data.Dataset`` the ALS / kNN trainers read, over ``lkpy_b200.data.Interactions``."""
+
+    def __init__(self, inter):
+        from lkpy_b200.components import Vocabulary
+
+        self._inter = inter
+        self.users = Vocabulary(inter.user_ids if inter.user_ids is not None else np.arange(inter.n_users), "user")
+        self.items = Vocabulary(inter.item_ids if inter.item_ids is not None else np.arange(inter.n_items), "item")
+
+    user_count = property(lambda self: self._inter.n_users)
+    item_count = property(lambda self: self._inter.n_items)
+
+    def interactions(self, *_a, **_kw):
+        return _Relationship(self._inter)
+
+
+def _module(name: str, package: bool = False, **attrs) -> types.ModuleType:
+    m = types.ModuleType(name)
+    if package:
+        m.__path__ = []  # a package without files: submodules are registered by hand
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def _load(name: str, rel: str) -> types.ModuleType:
+    spec = importlib.util.spec_from_file_location(name, REF_SRC / rel)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    parent, _, leaf = name.rpartition(".")
+    if parent in sys.modules:
+        setattr(sys.modules[parent], leaf, mod)
+    return mod
+
+
+@contextlib.contextmanager
+def reference_modules():
+    """Install the sandbox in ``sys.modules`` and yield ``{module name: module}``; removed again on exit."""
+    from lkpy_b200 import accel
+    from lkpy_b200.components import ItemList, RecQuery, Vocabulary
+
+    def ours(name):  # nothing of a real lenskit install may leak in or out
+        return name == "lenskit" or name.startswith("lenskit.") or name in ("structlog", "structlog.stdlib")
+
+    saved = {k: v for k, v in sys.modules.items() if ours(k)}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        _module("structlog", package=True, stdlib=_module("structlog.stdlib", BoundLogger=object))
+        _module("lenskit", package=True)
+        _module("lenskit.logging", package=True, get_logger=lambda *_a, **_k: _Log(), item_progress=_Progress,
+                Progress=_Progress, Stopwatch=_Stopwatch, trace=lambda *_a, **_k: None)  # fmt: skip
+        _module("lenskit.logging._resource", cur_memory=lambda: "0", max_memory=lambda: "0")
+        _module("lenskit.parallel", ensure_parallel_init=lambda: None, run_accel_task=accel.run_accel_task,
+                is_free_threaded=lambda: False)  # fmt: skip
+        sys.modules["lenskit._accel"] = accel  # the module the reference imports its kernels from
+        sys.modules["lenskit"]._accel = accel
+        from typing import Literal
+
+        _module("lenskit.data", package=True, Dataset=FakeDataset, ItemList=ItemList, RecQuery=RecQuery,
+                QueryInput=object, Vocabulary=Vocabulary, FeedbackType=Literal["explicit", "implicit"])  # fmt: skip
+        for pkg in ("lenskit.config", "lenskit.math", "lenskit.pipeline", "lenskit.als", "lenskit.knn"):
+            _module(pkg, package=True)
+        mods = {}
+        for name, rel in (
+            ("lenskit.diagnostics", "diagnostics.py"),
+            ("lenskit.lazy", "lazy.py"),
+            ("lenskit.data.types", "data/types.py"),
+            ("lenskit.data.matrix", "data/matrix.py"),
+            ("lenskit.config.common", "config/common.py"),
+            ("lenskit.math.solve", "math/solve.py"),
+            ("lenskit.random", "random.py"),
+            ("lenskit.pipeline._types", "pipeline/_types.py"),
+            ("lenskit.pipeline.components", "pipeline/components.py"),
+        ):
+            mods[name] = _load(name, rel)
+        sys.modules["lenskit.pipeline"].Component = mods["lenskit.pipeline.components"].Component
+        for name, rel in (
+            ("lenskit.training", "training.py"),
+            ("lenskit.als._common", "als/_common.py"),
+            ("lenskit.als._implicit", "als/_implicit.py"),
+            ("lenskit.knn.item", "knn/item.py"),
+        ):
+            mods[name] = _load(name, rel)
+        yield mods
+    finally:
+        import pyarrow as pa
+
+        for ext in ("lenskit.sparse_index", "lenskit.sparse_index_list", "lenskit.sparse_row"):
+            with contextlib.suppress(Exception):  # registered by data/matrix.py when it was loaded
+                pa.unregister_extension_type(ext)
+        for k in [k for k in sys.modules if ours(k)]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -209,3 +209,21 @@ def test_synthetic_matrix_cache_round_trip(tmp_path):
     other = data.synth_interactions_cached(f, n_users=300, n_items=150, nnz=5000)
     assert other.n_users == 300 and other.nnz == 5000
     assert data.synth_interactions_cached(None, **shape).nnz == c.nnz
+
+
+def test_own_index_type_matches_the_reference_wire_format():
+    """Without lenskit in the process the index field of a result carries this package's own class of the
+    ``lenskit.sparse_index`` extension type: same name, same JSON metadata (data/matrix.py:104-146), unregistered."""
+    import json
+    import sys
+
+    import pyarrow as pa
+
+    from lkpy_b200 import accel
+
+    if "lenskit.data.matrix" in sys.modules:
+        pytest.skip("lenskit is loaded: its own class is used")
+    t = accel.sparse_index_type(9066)
+    assert t.extension_name == "lenskit.sparse_index" and t.storage_type == pa.int32() and t.dimension == 9066
+    assert json.loads(t.__arrow_ext_serialize__().decode()) == {"dimension": 9066}
+    assert type(t).__arrow_ext_deserialize__(pa.int32(), t.__arrow_ext_serialize__()).dimension == 9066

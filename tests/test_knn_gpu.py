@@ -278,7 +278,11 @@ def test_accel_api_mirror(cuda_lib, ml_small):
     shape = (ml_small.n_users, ml_small.n_items)
     chunks = accel.run_accel_task(accel.knn.compute_similarities(a_ui, a_iu, shape, 1e-6, 20))
     assert isinstance(chunks, list) and all(pa.types.is_large_list(c.type) for c in chunks)
-    assert chunks[0].type.value_type == pa.struct([("index", pa.int32()), ("value", pa.float32())])
+    elem = chunks[0].type.value_type  # Struct{index: lenskit.sparse_index(n_items) over int32, value: float32}
+    assert [elem.field(i).name for i in range(elem.num_fields)] == ["index", "value"]
+    assert elem.field("index").type.extension_name == "lenskit.sparse_index"  # consumer.rs:109
+    assert elem.field("index").type.storage_type == pa.int32() and elem.field("index").type.dimension == ml_small.n_items
+    assert elem.field("value").type == pa.float32()
     smat = pa.chunked_array(chunks).combine_chunks()  # knn/item.py:173-177
     assert len(smat) == ml_small.n_items
     ref = oracle.knn_build(ui, iu, 1e-6, 20)

@@ -1,0 +1,144 @@
+"""
+The function-level drop-in of INTEGRATION.md §1 under the reference's OWN classes: ``lenskit.training``,
+``pipeline.components.Component``, ``data.matrix.SparseRowArray``, ``als._common`` / ``als._implicit`` and
+``knn.item`` are loaded from ``/root/reference`` (tests/ref_sandbox.py) with ``lenskit._accel`` bound to
+``lkpy_b200.accel``; ``scorer.train(dataset)`` then runs the reference's code down to the accelerator call.
+
+Build-container tests (``/root/reference`` does not travel to the GPU box, where they skip).  Without a CUDA
+device the device part of the two entry points is replaced by the oracle — everything else, Arrow ingest of
+the reference's containers, the task protocol, the in-place contract on ``this``, the result layout the
+reference's ``SparseRowArray.from_array`` has to accept, is the product code.
+"""
+
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import ref_sandbox
+from lkpy_b200 import accel, data
+
+pytestmark = pytest.mark.skipif(not ref_sandbox.available(), reason="needs the reference tree (build container only)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    with ref_sandbox.reference_modules() as mods, warnings.catch_warnings(), pytest.MonkeyPatch.context() as mp:
+        warnings.simplefilter("ignore")  # "not the short import path": the sandbox has no lenskit/__init__
+        if not torch.cuda.is_available():
+            _oracle_compute(mp)
+        yield mods
+
+
+def _oracle_compute(monkeypatch):
+    """No GPU here: keep the entry points' own argument handling, swap the device part for the oracle."""
+
+    def als_task(mode, matrix, this, other, otor, reg):
+        this = accel._check_factor("this", this, writable=True)
+        other = accel._check_factor("other", other)
+        csr = accel.as_host_csr(matrix)  # the reference's SparseRowArray
+        assert csr.shape == (this.shape[0], other.shape[0])
+
+        def run(_task):
+            new, delta = oracle.als_half("implicit", csr, this, other, otor_mat=otor)
+            this[...] = new  # in place, like implicit.rs:57-64
+            return float(delta)
+
+        return accel.AccelTask(run, total=this.shape[0])
+
+    def compute_similarities(ui_ratings, iu_ratings, shape, min_sim, save_nbrs):
+        nu, ni = shape
+        ui, iu = accel.as_host_csr(ui_ratings, ni), accel.as_host_csr(iu_ratings, nu)
+        assert ui.shape == (nu, ni) and iu.shape == (ni, nu)
+
+        def run(_task):
+            S = oracle.knn_build(ui, iu, min_sim, save_nbrs)
+            out = data.InteractionCSR(S.indptr.astype(np.int64), S.indices, S.data, (ni, ni))
+            return accel.csr_to_arrow_chunks(out, 2000)
+
+        return accel.AccelTask(run, total=ni)
+
+    monkeypatch.setattr(accel, "_als_task", als_task)
+    monkeypatch.setattr(accel.knn, "compute_similarities", compute_similarities)
+
+
+@pytest.fixture(scope="module")
+def ml_small():
+    return data.load_ml_small()
+
+
+def test_reference_implicit_mf_trains_through_the_shim(ref, ml_small):
+    """``ImplicitMFScorer.train`` (training.py:301-334 -> als/_common.py:209-256 -> als/_implicit.py:158-164):
+    the reference's trainer builds R and Rᵀ as SparseRowArrays, initialises the factors (items first) and
+    calls ``als.train_implicit_matrix`` once per half-epoch; the factors it ends with are those of the same
+    half-steps computed directly."""
+    imp, training = ref["lenskit.als._implicit"], ref["lenskit.training"]
+    k, epochs = 16, 2
+    m = imp.ImplicitMFScorer(embedding_size=k, epochs=epochs, regularization=0.1, weight=40)
+    assert type(m).train is training.UsesTrainer.train  # the reference's epoch loop, not ours
+    trainer = m.create_trainer(ref_sandbox.FakeDataset(ml_small), training.TrainingOptions(rng=42))
+    assert isinstance(trainer, imp.ImplicitMFTrainer)
+    assert type(trainer.ui_rates).__name__ == "SparseRowArray" and trainer.ui_rates.shape == (ml_small.n_users, ml_small.n_items)
+    p0, q0 = m.user_embeddings.copy(), m.item_embeddings.copy()
+    p_arr, q_arr = m.user_embeddings, m.item_embeddings
+    for _ in range(epochs):
+        metrics = trainer.train_epoch()
+        assert set(metrics) == {"deltaP", "deltaQ"} and all(np.isfinite(v) and v > 0 for v in metrics.values())
+    assert m.user_embeddings is p_arr and m.item_embeddings is q_arr  # mutated in place (TrainContext.left)
+    trainer.finalize()
+    assert m._OtOr.shape == (k, k)
+
+    ui, iu = data.als_implicit_matrices(ml_small, 40.0)
+    p, q = p0, q0
+    for _ in range(epochs):
+        p, _ = oracle.als_half("implicit", ui, p, q, otor_mat=imp._implicit_otor(q, 0.1))
+        q, _ = oracle.als_half("implicit", iu, q, p, otor_mat=imp._implicit_otor(p, 0.1))
+    tol = 1e-4 if torch.cuda.is_available() else 1e-6
+    assert np.linalg.norm(p_arr - p) <= tol * np.linalg.norm(p)
+    assert np.linalg.norm(q_arr - q) <= tol * np.linalg.norm(q)
+
+
+def test_reference_item_knn_trains_through_the_shim(ref, ml_small):
+    """``ItemKNNScorer.train`` (knn/item.py:121-199): the reference centres and normalises, hands two
+    SparseRowArrays to ``knn.compute_similarities``, concatenates the returned chunks and wraps them with
+    ``SparseRowArray.from_array`` — which only accepts an index field of the ``lenskit.sparse_index``
+    extension type (data/matrix.py:530-546).  The model it stores is the oracle's, bit for bit."""
+    knn, training = ref["lenskit.knn.item"], ref["lenskit.training"]
+    m = knn.ItemKNNScorer(max_nbrs=20, min_sim=1e-6, save_nbrs=20)
+    m.train(ref_sandbox.FakeDataset(ml_small), training.TrainingOptions())
+    sim = m.sim_matrix
+    assert type(sim).__name__ == "SparseRowArray" and sim.type.dimension == ml_small.n_items
+    ui, iu, means = data.knn_item_matrices(ml_small, True)
+    want = oracle.knn_build(ui, iu, 1e-6, 20)
+    got = sim.to_scipy()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert np.array_equal(got.data.view(np.int32), want.data.view(np.int32))
+    assert np.array_equal(np.asarray(m.item_means, dtype=np.float32).view(np.int32), means.view(np.int32))
+    assert np.array_equal(m.item_counts, np.diff(want.indptr))
+    # and the stored matrix goes back into the scoring entry points' ingest unchanged
+    back = accel.as_host_csr(sim, len(sim))
+    assert back.shape == (ml_small.n_items, ml_small.n_items) and np.array_equal(back.indices, want.indices)
+
+
+def test_result_index_field_is_the_reference_extension_type(ref):
+    """Wire format of the ``index`` field: extension name and JSON metadata of ``SparseIndexType``
+    (data/matrix.py:104-146), whether or not lenskit is loaded; it survives an IPC round trip."""
+    import pyarrow as pa
+
+    matrix = ref["lenskit.data.matrix"]
+    t_ref = accel.sparse_index_type(77)
+    assert isinstance(t_ref, matrix.SparseIndexType) and t_ref.dimension == 77  # lenskit loaded: its own class
+    csr = data.InteractionCSR(np.array([0, 2, 2, 3], np.int64), np.array([1, 5, 0], np.int32),
+                              np.array([0.5, 0.25, 1.0], np.float32), (3, 77))  # fmt: skip
+    arr = pa.chunked_array(accel.csr_to_arrow_chunks(csr, 2)).combine_chunks()
+    wrapped = matrix.SparseRowArray.from_array(arr)  # no external dimension: it must come from the type
+    assert wrapped.shape == (3, 77) and wrapped.to_scipy().nnz == 3
+    sink = pa.BufferOutputStream()
+    tbl = pa.table({"rows": arr})
+    with pa.ipc.new_stream(sink, tbl.schema) as w:
+        w.write_table(tbl)
+    col = pa.ipc.open_stream(sink.getvalue()).read_all().column("rows").combine_chunks()
+    assert isinstance(col.type.value_type.field("index").type, matrix.SparseIndexType)
+    assert col.type.value_type.field("index").type.dimension == 77
