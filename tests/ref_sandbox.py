@@ -1,13 +1,14 @@
 """
 Test harness: the reference's OWN Python classes for the hot path — ``lenskit.training``,
-``lenskit.pipeline.components.Component``, ``lenskit.data.matrix.SparseRowArray``,
-``lenskit.als._common / _implicit``, ``lenskit.knn.item`` — loaded from ``/root/reference`` file
+``lenskit.pipeline.components.Component``, ``lenskit.data.matrix.SparseRowArray``, ``ItemList``, ``Vocabulary``,
+``RecQuery``, ``lenskit.als._common / _implicit``, ``lenskit.knn.item`` — loaded from ``/root/reference`` file
 by file, with ``lenskit._accel`` bound to ``lkpy_b200.accel`` exactly as INTEGRATION.md §1 describes.
 
 The reference package cannot be imported as a whole here (its ``__init__`` needs ``lazy_loader`` /
 ``structlog``, its data layer needs the Rust extension's ``IDIndex`` / ``CoordinateTable``), so the modules
-the hot path does not touch are replaced by small fakes: logging, the parallel helpers, and the slice of
-``lenskit.data`` the two trainers read (``Dataset.interactions().matrix().scipy(...)``, the vocabularies).
+the hot path does not touch are replaced by small fakes: logging, the parallel helpers, Python stand-ins for
+the Rust helpers of the data model (``IDIndex``, ``scatter_array`` ...), and the slice of ``Dataset`` the two
+trainers read (``Dataset.interactions().matrix().scipy(...)``, the vocabularies).
 Everything between the user's ``scorer.train(dataset)`` and the accelerator call is the reference's code.
 
 Build-container only: ``/root/reference`` does not exist on the GPU box (the tests that use this skip there).
@@ -92,7 +93,7 @@ class FakeDataset:
     """The slice of ``lenskit.data.Dataset`` the ALS / kNN trainers read, over ``lkpy_b200.data.Interactions``."""
 
     def __init__(self, inter):
-        from lkpy_b200.components import Vocabulary
+        Vocabulary = sys.modules["lenskit.data"].Vocabulary  # the reference's own class (data/_vocab.py)
 
         self._inter = inter
         self.users = Vocabulary(inter.user_ids if inter.user_ids is not None else np.arange(inter.n_users), "user")
@@ -103,6 +104,73 @@ class FakeDataset:
 
     def interactions(self, *_a, **_kw):
         return _Relationship(self._inter)
+
+
+class IDIndex:
+    """Python stand-in for the Rust ``_accel.data.IDIndex`` (src/accel/data/index.rs:97-139) behind the
+    reference's real ``Vocabulary`` / ``ItemList``: id -> position; unknown (or wrongly typed) ids give None /
+    null."""
+
+    def __init__(self, ids=None):
+        import pyarrow as pa
+
+        self._ids = pa.array([], type=pa.int64()) if ids is None else (ids if isinstance(ids, pa.Array) else pa.array(ids))
+        self._pos = {v: i for i, v in enumerate(self._ids.to_pylist())}
+
+    def get_index(self, id_):
+        try:
+            if isinstance(id_, np.generic):
+                id_ = id_.item()
+            return self._pos.get(id_)
+        except TypeError:
+            return None
+
+    def get_indexes(self, ids):
+        import pyarrow as pa
+
+        vals = ids.to_pylist() if isinstance(ids, (pa.Array, pa.ChunkedArray)) else list(np.asarray(ids).tolist())
+        return pa.array([None if v is None else self._pos.get(v) for v in vals], type=pa.int32())
+
+    def id_array(self):
+        return self._ids
+
+    def __len__(self) -> int:
+        return len(self._ids)
+
+
+def _data_shims() -> types.SimpleNamespace:
+    """``lenskit._accel.data`` as far as ``data/_vocab.py``, ``_items.py`` and ``_mtarray.py`` use it."""
+    import hashlib
+
+    import pyarrow as pa
+
+    def hash_array(arr) -> str:
+        return hashlib.md5(repr(arr.to_pylist()).encode()).hexdigest()
+
+    def argsort_descending(scores):
+        v = scores.to_numpy(zero_copy_only=False).astype(np.float64)
+        order = np.argsort(-np.where(np.isnan(v), -np.inf, v), kind="stable")
+        return pa.array(order[~np.isnan(v[order])].astype(np.int32))
+
+    def argtopn(scores, n: int):
+        return argsort_descending(scores).slice(0, n)
+
+    def scatter_array_empty(dst_size: int, idx, src):
+        out = [None] * int(dst_size)
+        for i, v in zip(idx.to_pylist(), src.to_pylist()):
+            if i is not None:
+                out[i] = v
+        return pa.array(out, type=src.type)
+
+    def scatter_array(dst, idx, src):
+        out = dst.to_pylist()
+        for i, v in zip(idx.to_pylist(), src.to_pylist()):
+            if i is not None:
+                out[i] = v
+        return pa.array(out, type=dst.type)
+
+    return types.SimpleNamespace(IDIndex=IDIndex, hash_array=hash_array, argsort_descending=argsort_descending,
+                                 argtopn=argtopn, scatter_array=scatter_array, scatter_array_empty=scatter_array_empty)  # fmt: skip
 
 
 def _module(name: str, package: bool = False, **attrs) -> types.ModuleType:
@@ -130,7 +198,6 @@ def _load(name: str, rel: str) -> types.ModuleType:
 def reference_modules():
     """Install the sandbox in ``sys.modules`` and yield ``{module name: module}``; removed again on exit."""
     from lkpy_b200 import accel
-    from lkpy_b200.components import ItemList, RecQuery, Vocabulary
 
     def ours(name):  # nothing of a real lenskit install may leak in or out
         return name == "lenskit" or name.startswith("lenskit.") or name in ("structlog", "structlog.stdlib")
@@ -146,20 +213,28 @@ def reference_modules():
         _module("lenskit.logging._resource", cur_memory=lambda: "0", max_memory=lambda: "0")
         _module("lenskit.parallel", ensure_parallel_init=lambda: None, run_accel_task=accel.run_accel_task,
                 is_free_threaded=lambda: False)  # fmt: skip
-        sys.modules["lenskit._accel"] = accel  # the module the reference imports its kernels from
-        sys.modules["lenskit"]._accel = accel
+        # the module the reference imports its kernels from — als and knn are this package's;
+        # `data` (the Rust helpers of the reference's data model, outside the hot path) is a Python stand-in
+        sys.modules["lenskit"]._accel = _module("lenskit._accel", package=True, als=accel.als, knn=accel.knn,
+                                                data=_data_shims())  # fmt: skip
         from typing import Literal
 
-        _module("lenskit.data", package=True, Dataset=FakeDataset, ItemList=ItemList, RecQuery=RecQuery,
-                QueryInput=object, Vocabulary=Vocabulary, FeedbackType=Literal["explicit", "implicit"])  # fmt: skip
+        _module("lenskit.data", package=True, Dataset=FakeDataset, FeedbackType=Literal["explicit", "implicit"])
         for pkg in ("lenskit.config", "lenskit.math", "lenskit.pipeline", "lenskit.als", "lenskit.knn"):
             _module(pkg, package=True)
         mods = {}
         for name, rel in (
             ("lenskit.diagnostics", "diagnostics.py"),
             ("lenskit.lazy", "lazy.py"),
+            ("lenskit.torch", "torch.py"),
             ("lenskit.data.types", "data/types.py"),
             ("lenskit.data.matrix", "data/matrix.py"),
+            ("lenskit.data._checks", "data/_checks.py"),
+            ("lenskit.data._mtarray", "data/_mtarray.py"),
+            ("lenskit.data._arrow", "data/_arrow.py"),
+            ("lenskit.data._vocab", "data/_vocab.py"),
+            ("lenskit.data._items", "data/_items.py"),
+            ("lenskit.data._query", "data/_query.py"),
             ("lenskit.config.common", "config/common.py"),
             ("lenskit.math.solve", "math/solve.py"),
             ("lenskit.random", "random.py"),
@@ -168,6 +243,10 @@ def reference_modules():
         ):
             mods[name] = _load(name, rel)
         sys.modules["lenskit.pipeline"].Component = mods["lenskit.pipeline.components"].Component
+        dpk = sys.modules["lenskit.data"]
+        dpk.Vocabulary, dpk.ItemList = mods["lenskit.data._vocab"].Vocabulary, mods["lenskit.data._items"].ItemList
+        dpk.RecQuery, dpk.QueryInput = mods["lenskit.data._query"].RecQuery, mods["lenskit.data._query"].QueryInput
+        dpk.ID = mods["lenskit.data.types"].ID
         for name, rel in (
             ("lenskit.training", "training.py"),
             ("lenskit.als._common", "als/_common.py"),

@@ -14,6 +14,7 @@ import warnings
 
 import numpy as np
 import pytest
+import scipy.sparse as sps
 import torch
 
 import oracle
@@ -60,8 +61,26 @@ def _oracle_compute(monkeypatch):
 
         return accel.AccelTask(run, total=ni)
 
+    class CpuScorerState:
+        """``engine.KnnScorerState`` with the oracle behind ``score``: accel._score runs unchanged around it."""
+
+        def __init__(self, n_items, indptr, cols, vals):
+            self.S = sps.csr_array((np.asarray(vals), np.asarray(cols), np.asarray(indptr)), shape=(n_items, n_items))
+
+        @classmethod
+        def create(cls, n_items, indptr, cols, vals, _dev, user_mode=False):
+            assert not user_mode
+            return cls(n_items, indptr, cols, vals)
+
+        def score(self, _ref_ptr, ref_items, ref_vals, _tgt_ptr, tgt_items, max_nbrs, min_nbrs):
+            sc, ct = oracle.knn_score(self.S, ref_items.numpy(), None if ref_vals is None else ref_vals.numpy(),
+                                      tgt_items.numpy(), max_nbrs, min_nbrs)  # fmt: skip
+            return torch.from_numpy(sc), torch.from_numpy(ct)
+
     monkeypatch.setattr(accel, "_als_task", als_task)
     monkeypatch.setattr(accel.knn, "compute_similarities", compute_similarities)
+    monkeypatch.setattr(accel._lib, "require_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(accel.engine, "KnnScorerState", CpuScorerState)
 
 
 @pytest.fixture(scope="module")
@@ -142,3 +161,51 @@ def test_result_index_field_is_the_reference_extension_type(ref):
     col = pa.ipc.open_stream(sink.getvalue()).read_all().column("rows").combine_chunks()
     assert isinstance(col.type.value_type.field("index").type, matrix.SparseIndexType)
     assert col.type.value_type.field("index").type.dimension == 77
+
+
+def test_reference_item_knn_scores_through_the_shim(ref, ml_small):
+    """``ItemKNNScorer.__call__`` (knn/item.py:230-295) with the reference's real ``ItemList`` / ``Vocabulary``:
+    nullable Int32 / Float32 Arrow arrays in (unknown history items and unknown targets are nulls), nullable
+    score and count arrays out, the means added back by the reference; equal to the oracle's accumulator."""
+    knn, training, items_mod = ref["lenskit.knn.item"], ref["lenskit.training"], ref["lenskit.data._items"]
+    ItemList = items_mod.ItemList
+    m = knn.ItemKNNScorer(max_nbrs=20, min_sim=1e-6, save_nbrs=20)
+    ds = ref_sandbox.FakeDataset(ml_small)
+    m.train(ds, training.TrainingOptions())
+    accel.clear_cache()
+    R = ml_small.coo().tocsr()
+    u = int(np.argmax(np.diff(R.indptr)))
+    nums = R.indices[R.indptr[u] : R.indptr[u + 1]]
+    rates = R.data[R.indptr[u] : R.indptr[u + 1]].astype(np.float32)
+    unknown = int(ml_small.item_ids.max()) + 1000
+    hist = ItemList(item_ids=np.concatenate([ml_small.item_ids[nums], [unknown]]), rating=np.concatenate([rates, [3.0]]))
+    tgt_nums = np.arange(0, ml_small.n_items, 7)
+    targets = ItemList(item_ids=np.concatenate([ml_small.item_ids[tgt_nums], [unknown + 1]]))
+    out = m(hist, targets)
+    got = out.scores("numpy")
+    counts = out.field("nbr_counts", "numpy")
+    assert len(got) == len(tgt_nums) + 1 and np.isnan(got[-1])  # the unknown target has no score
+
+    ui, iu, means = data.knn_item_matrices(ml_small, True)
+    S = oracle.knn_build(ui, iu, 1e-6, 20)
+    rv = (rates - means[nums]).astype(np.float32)
+    want, want_ct = oracle.knn_score(S, nums.astype(np.int32), rv, tgt_nums.astype(np.int32), 20, 1)
+    ok = ~np.isnan(want)
+    assert ok.sum() > 100 and np.array_equal(np.isnan(got[:-1]), ~ok)
+    assert np.array_equal((want[ok] + means[tgt_nums[ok]]).astype(np.float32).view(np.int32),
+                          got[:-1][ok].astype(np.float32).view(np.int32))  # fmt: skip
+    assert np.array_equal(np.asarray(counts[:-1], dtype=np.float64)[ok], want_ct[ok].astype(np.float64))
+
+
+def test_reference_implicit_mf_scores_after_training_through_the_shim(ref, ml_small):
+    """The model the reference's trainer leaves behind is the one its own ``ALSBase.__call__`` scores with
+    (als/_common.py:133-175): known user -> P[u] . Q^T over the requested items."""
+    imp, training, items_mod = ref["lenskit.als._implicit"], ref["lenskit.training"], ref["lenskit.data._items"]
+    m = imp.ImplicitMFScorer(embedding_size=8, epochs=1, regularization=0.1, weight=40)
+    m.train(ref_sandbox.FakeDataset(ml_small), training.TrainingOptions(rng=7))
+    assert m.trained_epochs == 1 and m.user_embeddings.dtype == np.float32
+    uid = ml_small.user_ids[5]
+    tgt = np.array([0, 10, 200, 4000])
+    out = m(uid, items_mod.ItemList(item_ids=ml_small.item_ids[tgt]))
+    want = m.item_embeddings[tgt] @ m.user_embeddings[5]
+    assert np.allclose(out.scores("numpy"), want, rtol=1e-5, atol=1e-7)
