@@ -1,7 +1,7 @@
 """
 Test harness: the reference's OWN Python classes for the hot path — ``lenskit.training``,
 ``lenskit.pipeline.components.Component``, ``lenskit.data.matrix.SparseRowArray``, ``ItemList``, ``Vocabulary``,
-``RecQuery``, ``lenskit.als._common / _implicit``, ``lenskit.knn.item`` — loaded from ``/root/reference`` file
+``RecQuery``, ``basic.bias.BiasModel``, ``lenskit.als._common / _implicit / _explicit``, ``lenskit.knn.item / user`` — loaded from ``/root/reference`` file
 by file, with ``lenskit._accel`` bound to ``lkpy_b200.accel`` exactly as INTEGRATION.md §1 describes.
 
 The reference package cannot be imported as a whole here (its ``__init__`` needs ``lazy_loader`` /
@@ -101,6 +101,11 @@ class FakeDataset:
 
     user_count = property(lambda self: self._inter.n_users)
     item_count = property(lambda self: self._inter.n_items)
+    interaction_count = property(lambda self: self._inter.nnz)
+
+    def interaction_matrix(self, *, format: str = "scipy", layout: str = "csr", field: str | None = None, **_kw):
+        assert format == "scipy"
+        return _MatrixView(self._inter).scipy(field, layout=layout)
 
     def interactions(self, *_a, **_kw):
         return _Relationship(self._inter)
@@ -211,8 +216,9 @@ def reference_modules():
         _module("lenskit.logging", package=True, get_logger=lambda *_a, **_k: _Log(), item_progress=_Progress,
                 Progress=_Progress, Stopwatch=_Stopwatch, trace=lambda *_a, **_k: None)  # fmt: skip
         _module("lenskit.logging._resource", cur_memory=lambda: "0", max_memory=lambda: "0")
-        _module("lenskit.parallel", ensure_parallel_init=lambda: None, run_accel_task=accel.run_accel_task,
-                is_free_threaded=lambda: False)  # fmt: skip
+        _module("lenskit.parallel", package=True, ensure_parallel_init=lambda: None,
+                run_accel_task=accel.run_accel_task, is_free_threaded=lambda: False)  # fmt: skip
+        _module("lenskit.parallel.config", ensure_parallel_init=lambda: None)
         # the module the reference imports its kernels from — als and knn are this package's;
         # `data` (the Rust helpers of the reference's data model, outside the hot path) is a Python stand-in
         sys.modules["lenskit"]._accel = _module("lenskit._accel", package=True, als=accel.als, knn=accel.knn,
@@ -220,7 +226,7 @@ def reference_modules():
         from typing import Literal
 
         _module("lenskit.data", package=True, Dataset=FakeDataset, FeedbackType=Literal["explicit", "implicit"])
-        for pkg in ("lenskit.config", "lenskit.math", "lenskit.pipeline", "lenskit.als", "lenskit.knn"):
+        for pkg in ("lenskit.config", "lenskit.math", "lenskit.pipeline", "lenskit.als", "lenskit.knn", "lenskit.basic"):
             _module(pkg, package=True)
         mods = {}
         for name, rel in (
@@ -249,9 +255,17 @@ def reference_modules():
         dpk.ID = mods["lenskit.data.types"].ID
         for name, rel in (
             ("lenskit.training", "training.py"),
+            ("lenskit.basic.bias", "basic/bias.py"),
+        ):
+            mods[name] = _load(name, rel)
+        sys.modules["lenskit.basic"].BiasModel = mods["lenskit.basic.bias"].BiasModel
+        sys.modules["lenskit.basic"].Damping = mods["lenskit.basic.bias"].Damping
+        for name, rel in (
             ("lenskit.als._common", "als/_common.py"),
             ("lenskit.als._implicit", "als/_implicit.py"),
+            ("lenskit.als._explicit", "als/_explicit.py"),
             ("lenskit.knn.item", "knn/item.py"),
+            ("lenskit.knn.user", "knn/user.py"),
         ):
             mods[name] = _load(name, rel)
         yield mods

@@ -43,7 +43,10 @@ def _oracle_compute(monkeypatch):
         assert csr.shape == (this.shape[0], other.shape[0])
 
         def run(_task):
-            new, delta = oracle.als_half("implicit", csr, this, other, otor_mat=otor)
+            if mode == accel._lib.LK_ALS_IMPLICIT:
+                new, delta = oracle.als_half("implicit", csr, this, other, otor_mat=otor)
+            else:
+                new, delta = oracle.als_half("explicit", csr, this, other, reg=reg)
             this[...] = new  # in place, like implicit.rs:57-64
             return float(delta)
 
@@ -64,17 +67,24 @@ def _oracle_compute(monkeypatch):
     class CpuScorerState:
         """``engine.KnnScorerState`` with the oracle behind ``score``: accel._score runs unchanged around it."""
 
-        def __init__(self, n_items, indptr, cols, vals):
-            self.S = sps.csr_array((np.asarray(vals), np.asarray(cols), np.asarray(indptr)), shape=(n_items, n_items))
+        def __init__(self, n_items, indptr, cols, vals, user_mode):
+            n_rows = len(indptr) - 1
+            self.explicit = vals is not None
+            v = np.asarray(vals) if vals is not None else np.ones(len(cols), np.float32)
+            self.S = sps.csr_array((v, np.asarray(cols), np.asarray(indptr)), shape=(n_rows, n_items))
+            self.user_mode = user_mode
 
         @classmethod
         def create(cls, n_items, indptr, cols, vals, _dev, user_mode=False):
-            assert not user_mode
-            return cls(n_items, indptr, cols, vals)
+            return cls(n_items, indptr, cols, vals, user_mode)
 
         def score(self, _ref_ptr, ref_items, ref_vals, _tgt_ptr, tgt_items, max_nbrs, min_nbrs):
-            sc, ct = oracle.knn_score(self.S, ref_items.numpy(), None if ref_vals is None else ref_vals.numpy(),
-                                      tgt_items.numpy(), max_nbrs, min_nbrs)  # fmt: skip
+            if self.user_mode:  # the "history" is the neighbour list and carries the weights (user_score.rs:21-98)
+                sc, ct = oracle.user_score(self.S, ref_items.numpy(), ref_vals.numpy(), tgt_items.numpy(), max_nbrs,
+                                           min_nbrs, explicit=self.explicit)  # fmt: skip
+            else:
+                sc, ct = oracle.knn_score(self.S, ref_items.numpy(), None if ref_vals is None else ref_vals.numpy(),
+                                          tgt_items.numpy(), max_nbrs, min_nbrs)  # fmt: skip
             return torch.from_numpy(sc), torch.from_numpy(ct)
 
     monkeypatch.setattr(accel, "_als_task", als_task)
@@ -163,15 +173,16 @@ def test_result_index_field_is_the_reference_extension_type(ref):
     assert col.type.value_type.field("index").type.dimension == 77
 
 
-def test_reference_item_knn_scores_through_the_shim(ref, ml_small):
+@pytest.mark.parametrize("feedback", ["explicit", "implicit"])
+def test_reference_item_knn_scores_through_the_shim(ref, ml_small, feedback):
     """``ItemKNNScorer.__call__`` (knn/item.py:230-295) with the reference's real ``ItemList`` / ``Vocabulary``:
     nullable Int32 / Float32 Arrow arrays in (unknown history items and unknown targets are nulls), nullable
     score and count arrays out, the means added back by the reference; equal to the oracle's accumulator."""
     knn, training, items_mod = ref["lenskit.knn.item"], ref["lenskit.training"], ref["lenskit.data._items"]
     ItemList = items_mod.ItemList
-    m = knn.ItemKNNScorer(max_nbrs=20, min_sim=1e-6, save_nbrs=20)
-    ds = ref_sandbox.FakeDataset(ml_small)
-    m.train(ds, training.TrainingOptions())
+    explicit = feedback == "explicit"
+    m = knn.ItemKNNScorer(max_nbrs=20, min_sim=1e-6, save_nbrs=20, feedback=feedback)
+    m.train(ref_sandbox.FakeDataset(ml_small), training.TrainingOptions())
     accel.clear_cache()
     R = ml_small.coo().tocsr()
     u = int(np.argmax(np.diff(R.indptr)))
@@ -186,14 +197,15 @@ def test_reference_item_knn_scores_through_the_shim(ref, ml_small):
     counts = out.field("nbr_counts", "numpy")
     assert len(got) == len(tgt_nums) + 1 and np.isnan(got[-1])  # the unknown target has no score
 
-    ui, iu, means = data.knn_item_matrices(ml_small, True)
+    ui, iu, means = data.knn_item_matrices(ml_small, explicit)
     S = oracle.knn_build(ui, iu, 1e-6, 20)
-    rv = (rates - means[nums]).astype(np.float32)
+    rv = (rates - means[nums]).astype(np.float32) if explicit else None
     want, want_ct = oracle.knn_score(S, nums.astype(np.int32), rv, tgt_nums.astype(np.int32), 20, 1)
     ok = ~np.isnan(want)
     assert ok.sum() > 100 and np.array_equal(np.isnan(got[:-1]), ~ok)
-    assert np.array_equal((want[ok] + means[tgt_nums[ok]]).astype(np.float32).view(np.int32),
-                          got[:-1][ok].astype(np.float32).view(np.int32))  # fmt: skip
+    if explicit:
+        want = want + means[tgt_nums]
+    assert np.array_equal(want[ok].astype(np.float32).view(np.int32), got[:-1][ok].astype(np.float32).view(np.int32))
     assert np.array_equal(np.asarray(counts[:-1], dtype=np.float64)[ok], want_ct[ok].astype(np.float64))
 
 
@@ -209,3 +221,56 @@ def test_reference_implicit_mf_scores_after_training_through_the_shim(ref, ml_sm
     out = m(uid, items_mod.ItemList(item_ids=ml_small.item_ids[tgt]))
     want = m.item_embeddings[tgt] @ m.user_embeddings[5]
     assert np.allclose(out.scores("numpy"), want, rtol=1e-5, atol=1e-7)
+
+
+def test_reference_biased_mf_trains_through_the_shim(ref, ml_small):
+    """``BiasedMFScorer`` (als/_explicit.py:94-118): the reference learns its bias model, builds the residual
+    matrices and calls ``als.train_explicit_matrix(matrix, this, other, reg)`` — the scalar ``reg`` (scaled by
+    the row's nnz inside, explicit.rs:104-108) instead of a Gram; then scores with its own ``__call__``."""
+    exp, training, items_mod = ref["lenskit.als._explicit"], ref["lenskit.training"], ref["lenskit.data._items"]
+    m = exp.BiasedMFScorer(embedding_size=8, epochs=2, regularization=0.1, damping=5.0)
+    trainer = m.create_trainer(ref_sandbox.FakeDataset(ml_small), training.TrainingOptions(rng=3))
+    p, q = m.user_embeddings.copy(), m.item_embeddings.copy()
+    p_arr, q_arr = m.user_embeddings, m.item_embeddings
+    for _ in range(2):
+        trainer.train_epoch()
+    ui, iu = accel.as_host_csr(trainer.ui_rates), accel.as_host_csr(trainer.iu_rates)
+    assert ui.shape == (ml_small.n_users, ml_small.n_items) and iu.shape == ui.shape[::-1]
+    for _ in range(2):
+        p, _ = oracle.als_half("explicit", ui, p, q, reg=trainer.u_ctx.reg)
+        q, _ = oracle.als_half("explicit", iu, q, p, reg=trainer.i_ctx.reg)
+    tol = 1e-4 if torch.cuda.is_available() else 1e-6
+    assert np.linalg.norm(p_arr - p) <= tol * np.linalg.norm(p) and np.linalg.norm(q_arr - q) <= tol * np.linalg.norm(q)
+    trainer.finalize()
+    out = m(ml_small.user_ids[3], items_mod.ItemList(item_ids=ml_small.item_ids[[1, 50, 900]]))
+    assert np.all(np.isfinite(out.scores("numpy")))
+
+
+@pytest.mark.parametrize("feedback", ["explicit", "implicit"])
+def test_reference_user_knn_scores_through_the_shim(ref, ml_small, feedback):
+    """``UserKNNScorer.__call__`` (knn/user.py:157-255) -> ``knn.user_score_items_explicit / _implicit``
+    (user_score.rs:21-98): the neighbour list (Int32 rows, Float32 similarities) and the reference's own
+    ``user_ratings`` SparseRowArray go in, a nullable Float32 array comes out, the user mean is added by the
+    reference; equal to the oracle's accumulator on the same neighbour list."""
+    usr, training, items_mod = ref["lenskit.knn.user"], ref["lenskit.training"], ref["lenskit.data._items"]
+    m = usr.UserKNNScorer(max_nbrs=15, min_nbrs=2, min_sim=1e-6, feedback=feedback)
+    m.train(ref_sandbox.FakeDataset(ml_small), training.TrainingOptions())
+    accel.clear_cache()
+    uidx = 42
+    tgt = np.arange(0, ml_small.n_items, 11)
+    out = m(ml_small.user_ids[uidx], items_mod.ItemList(item_ids=ml_small.item_ids[tgt]))
+    got = out.scores("numpy")
+
+    # the neighbour list exactly as the reference builds it (user.py:183-200), then the oracle
+    _uidx, ratings, umean = m._get_user_data(ref["lenskit.data._query"].RecQuery.create(ml_small.user_ids[uidx]))
+    sims = m.user_vectors @ ratings
+    sims[uidx] = 0
+    mask = sims >= m.config.min_sim
+    rat = accel.as_host_csr(m.user_ratings)  # implicit feedback: a structure-only SparseRowArray
+    rat = sps.csr_array((rat.values, rat.indices, rat.indptr), shape=rat.shape)
+    want, _ct = oracle.user_score(rat, np.arange(len(sims), dtype=np.int32)[mask],
+                                  sims[mask].astype(np.float32), tgt.astype(np.int32), 15, 2,
+                                  explicit=feedback == "explicit")  # fmt: skip
+    ok = ~np.isnan(want)
+    assert ok.sum() > 50 and np.array_equal(np.isnan(got), ~ok)
+    assert np.array_equal((want[ok] + np.float32(umean)).astype(np.float32).view(np.int32), got[ok].astype(np.float32).view(np.int32))
