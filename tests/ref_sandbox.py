@@ -6,7 +6,8 @@ by file, with ``lenskit._accel`` bound to ``lkpy_b200.accel`` exactly as INTEGRA
 
 The reference package cannot be imported as a whole here (its ``__init__`` needs ``lazy_loader`` /
 ``structlog``, its data layer needs the Rust extension's ``IDIndex`` / ``CoordinateTable``), so the modules
-the hot path does not touch are replaced by small fakes: logging, the parallel helpers, Python stand-ins for
+the hot path does not touch are replaced by small fakes: logging, the thread-pool configuration (the task
+runner itself, ``parallel/_task.py``, is the reference's), Python stand-ins for
 the Rust helpers of the data model (``IDIndex``, ``scatter_array`` ...), and the slice of ``Dataset`` the two
 trainers read (``Dataset.interactions().matrix().scipy(...)``, the vocabularies).
 Everything between the user's ``scorer.train(dataset)`` and the accelerator call is the reference's code.
@@ -52,6 +53,23 @@ class _Log:
 class _Stopwatch:
     def __str__(self):
         return "0s"
+
+
+class _AtomicInt:
+    """``_accel.AtomicInt`` as parallel/_task.py uses it (thread names)."""
+
+    def __init__(self):
+        self._v = 0
+
+    def fetch_add(self, n: int = 1) -> int:
+        v, self._v = self._v, self._v + n
+        return v
+
+
+class _NestedPool:
+    @staticmethod
+    def active_accel_pool():
+        return None
 
 
 class _Progress:
@@ -216,13 +234,17 @@ def reference_modules():
         _module("lenskit.logging", package=True, get_logger=lambda *_a, **_k: _Log(), item_progress=_Progress,
                 Progress=_Progress, Stopwatch=_Stopwatch, trace=lambda *_a, **_k: None)  # fmt: skip
         _module("lenskit.logging._resource", cur_memory=lambda: "0", max_memory=lambda: "0")
-        _module("lenskit.parallel", package=True, ensure_parallel_init=lambda: None,
-                run_accel_task=accel.run_accel_task, is_free_threaded=lambda: False)  # fmt: skip
+        par = _module("lenskit.parallel", package=True, ensure_parallel_init=lambda: None,
+                      is_free_threaded=lambda: False)  # fmt: skip
         _module("lenskit.parallel.config", ensure_parallel_init=lambda: None)
+        _module("lenskit.parallel._pool", NestedPool=_NestedPool)
         # the module the reference imports its kernels from — als and knn are this package's;
         # `data` (the Rust helpers of the reference's data model, outside the hot path) is a Python stand-in
         sys.modules["lenskit"]._accel = _module("lenskit._accel", package=True, als=accel.als, knn=accel.knn,
-                                                data=_data_shims())  # fmt: skip
+                                                data=_data_shims(), AtomicInt=_AtomicInt,
+                                                NestedAccelPool=object)  # fmt: skip
+        # the reference's own task runner (parallel/_task.py:25-135) drives this package's AccelTask objects
+        par.run_accel_task = _load("lenskit.parallel._task", "parallel/_task.py").run_accel_task
         from typing import Literal
 
         _module("lenskit.data", package=True, Dataset=FakeDataset, FeedbackType=Literal["explicit", "implicit"])

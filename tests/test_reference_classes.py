@@ -274,3 +274,37 @@ def test_reference_user_knn_scores_through_the_shim(ref, ml_small, feedback):
     ok = ~np.isnan(want)
     assert ok.sum() > 50 and np.array_equal(np.isnan(got), ~ok)
     assert np.array_equal((want[ok] + np.float32(umean)).astype(np.float32).view(np.int32), got[ok].astype(np.float32).view(np.int32))
+
+
+def test_reference_task_runner_drives_the_task_mirror(ref):
+    """The reference's own ``run_accel_task`` (parallel/_task.py:25-57) over this package's ``AccelTask``:
+    result hand-back, ``invoke(pool=...)`` on its worker thread, failures re-raised as its RuntimeError with the
+    task's exception as the cause, progress tuples forwarded to the progress object."""
+    import sys
+    import threading
+    import time
+
+    run = sys.modules["lenskit.parallel"].run_accel_task
+    assert run.__module__ == "lenskit.parallel._task"
+    seen = {}
+
+    def body(task):
+        seen["thread"] = threading.current_thread().name
+        time.sleep(0.5)  # long enough for two polls of current_progress()
+        return 42.0
+
+    prog = ref_sandbox._Progress()
+    assert run(accel.AccelTask(body, total=10), progress=prog) == 42.0
+    assert seen["thread"].startswith("AccelTask-") and prog.updates >= 1
+
+    def boom(_task):
+        raise RuntimeError("ALS solve error: array minor of row 3 is not positive")
+
+    with pytest.raises(RuntimeError, match="accelerator task failed") as ei:
+        run(accel.AccelTask(boom, total=1))
+    assert "ALS solve error" in str(ei.value.__cause__)
+    t = accel.AccelTask(body, total=1)
+    t.cancel()
+    with pytest.raises(RuntimeError, match="accelerator task failed") as ei:
+        run(t)
+    assert "cancelled" in str(ei.value.__cause__)
