@@ -513,15 +513,20 @@ def user_score_items_implicit(tgt_items, nbr_rows, nbr_sims, ratings, max_nbrs: 
     return _user_score(tgt_items, nbr_rows, nbr_sims, ratings, max_nbrs, min_nbrs, False)
 
 
-def argtopn(scores: Any, n: int) -> np.ndarray:
+def argtopn(scores: Any, n: int):
     """
     ``_accel.data.argtopn`` (src/accel/data/sorting.rs:131-170): indices of the ``n`` largest non-NaN
     (and non-null) scores, in the reference's order.  One vector is one thread's work for
     ``lk_topn_columns`` — this entry point exists for interface parity; batches go through
     ``argtopn_batch`` / ``ALSBase.recommend_batch``.
     """
-    s = _to_f32(scores)
-    return argtopn_batch(s[None, :], n)[0]
+    s = _to_f32_nan(scores)  # Arrow nulls are skipped like NaNs (`scores.is_valid(i) && accept(...)`, sorting.rs:163-167)
+    idx = argtopn_batch(s[None, :], n)[0]
+    if hasattr(scores, "null_count") and hasattr(scores, "to_numpy"):  # Arrow in, Arrow Int32Array out, like the reference
+        import pyarrow as pa
+
+        return pa.array(idx, type=pa.int32())
+    return idx
 
 
 def argtopn_batch(scores: Any, n: int) -> list[np.ndarray]:

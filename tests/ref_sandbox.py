@@ -175,8 +175,10 @@ def _data_shims() -> types.SimpleNamespace:
         order = np.argsort(-np.where(np.isnan(v), -np.inf, v), kind="stable")
         return pa.array(order[~np.isnan(v[order])].astype(np.int32))
 
-    def argtopn(scores, n: int):
-        return argsort_descending(scores).slice(0, n)
+    def argtopn(scores, n: int):  # the step after the scorers: this package's mirror
+        from lkpy_b200 import accel
+
+        return accel.argtopn(scores, n)
 
     def scatter_array_empty(dst_size: int, idx, src):
         out = [None] * int(dst_size)

@@ -87,6 +87,10 @@ def _oracle_compute(monkeypatch):
                                           tgt_items.numpy(), max_nbrs, min_nbrs)  # fmt: skip
             return torch.from_numpy(sc), torch.from_numpy(ct)
 
+    def argtopn_batch(scores, n):
+        return [oracle.argtopn(np.ascontiguousarray(row, dtype=np.float32), int(min(n, len(row)))) for row in np.asarray(scores)]
+
+    monkeypatch.setattr(accel, "argtopn_batch", argtopn_batch)
     monkeypatch.setattr(accel, "_als_task", als_task)
     monkeypatch.setattr(accel.knn, "compute_similarities", compute_similarities)
     monkeypatch.setattr(accel._lib, "require_device", lambda: torch.device("cpu"))
@@ -308,3 +312,24 @@ def test_reference_task_runner_drives_the_task_mirror(ref):
     with pytest.raises(RuntimeError, match="accelerator task failed") as ei:
         run(t)
     assert "cancelled" in str(ei.value.__cause__)
+
+
+def test_reference_item_list_top_n_through_the_argtopn_mirror(ref):
+    """``ItemList.top_n`` (data/_items.py:942-998) -> ``_accel.data.argtopn(scores: pa.Array, n)``: Arrow nulls
+    and NaNs are both unscored (sorting.rs:163-167), an Int32Array of positions comes back, best first."""
+    import pyarrow as pa
+
+    ItemList = ref["lenskit.data._items"].ItemList
+    rng = np.random.default_rng(8)
+    scores = rng.standard_normal(200).astype(np.float32)
+    scores[::9] = np.nan
+    il = ItemList(item_ids=np.arange(1000, 1200), scores=scores)
+    top = il.top_n(10)
+    want = oracle.argtopn(scores, 10)
+    assert top.ids().tolist() == (1000 + want).tolist() and top.ordered
+    # nullable Arrow scores, as the kNN entry points return them
+    masked = np.zeros(200, dtype=bool)
+    masked[::4] = True
+    got = accel.argtopn(pa.array(scores, mask=masked), 25)
+    assert isinstance(got, pa.Array) and got.type == pa.int32()
+    assert got.to_numpy().tolist() == oracle.argtopn(np.where(masked, np.nan, scores).astype(np.float32), 25).tolist()

@@ -119,6 +119,15 @@ def test_gpu_topn_strided_view_and_api_mirror():
     rows = accel.data.argtopn_batch(s.T[:8], 40)
     for r in range(8):
         assert np.array_equal(rows[r], oracle.argtopn(s[:, r], 40))
+    # a nullable Arrow vector (what the kNN entry points return): nulls are unscored like NaNs
+    # (sorting.rs:163-167), and the answer is an Int32Array like the reference's
+    import pyarrow as pa
+
+    masked = np.zeros(len(v), dtype=bool)
+    masked[::5] = True
+    got = accel.data.argtopn(pa.array(v, mask=masked), 25)
+    assert isinstance(got, pa.Array) and got.type == pa.int32()
+    assert got.to_numpy().tolist() == oracle.argtopn(np.where(masked, np.nan, v).astype(np.float32), 25).tolist()
     with pytest.raises(ValueError):
         engine.topn_columns(d, 0)
     with pytest.raises(ValueError):
