@@ -333,3 +333,33 @@ def test_reference_item_list_top_n_through_the_argtopn_mirror(ref):
     got = accel.argtopn(pa.array(scores, mask=masked), 25)
     assert isinstance(got, pa.Array) and got.type == pa.int32()
     assert got.to_numpy().tolist() == oracle.argtopn(np.where(masked, np.nan, scores).astype(np.float32), 25).tolist()
+
+
+def test_integration_md_trainer_binding_matches_both_sides(ref):
+    """The trainer-level binding printed in INTEGRATION.md §2 is executed here as far as a machine without a GPU
+    can: the code block is compiled, its classes are created on top of the reference's real ``ImplicitMFTrainer``
+    / ``ImplicitMFScorer``, every ``engine.*`` / ``_lib.*`` name it uses exists in this package, and every
+    ``context.*`` field it reads exists on the reference's ``TrainContext``."""
+    import ast
+    import re
+    from pathlib import Path
+
+    from lkpy_b200 import _lib, engine
+
+    text = (Path(__file__).resolve().parent.parent / "INTEGRATION.md").read_text()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    block = next(b for b in blocks if "class B200ImplicitMFTrainer" in b)
+    tree = ast.parse(block)
+    ns: dict = {}
+    exec(compile(tree, "INTEGRATION.md#trainer-binding", "exec"), ns)  # imports lenskit.als._implicit: the sandbox's
+    imp = ref["lenskit.als._implicit"]
+    assert issubclass(ns["B200ImplicitMFTrainer"], imp.ImplicitMFTrainer)
+    assert issubclass(ns["B200ImplicitMFScorer"], imp.ImplicitMFScorer)
+    assert not getattr(ns["B200ImplicitMFTrainer"], "__abstractmethods__", None)  # the hook is the only abstract piece it fills
+    used = {(n.value.id, n.attr) for n in ast.walk(tree) if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name)}
+    for mod_name, mod in (("engine", engine), ("_lib", _lib)):
+        for _m, attr in sorted(u for u in used if u[0] == mod_name):
+            assert hasattr(mod, attr), f"INTEGRATION.md uses {mod_name}.{attr}, which does not exist"
+    fields = set(ref["lenskit.als._common"].TrainContext._fields)
+    for _m, attr in sorted(u for u in used if u[0] in ("context", "ctx")):
+        assert attr in fields, f"INTEGRATION.md reads context.{attr}; TrainContext has {sorted(fields)}"
